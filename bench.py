@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the HashNeRF hot path on B200 (contract: see DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours       one "step" = one training iteration of BASELINE config 3 on every rank: 65536 rays/rank,
+           64+128 samples, 16 levels, T=2^19, finest 512 -> render fwd (coarse+fine), image+sparsity+TV
+           losses, backward, gradient all-reduce (N>1), RAdam.  `value` = rays/s with the ray batch already
+           in HBM; `e2e` = the same through the public API with pinned-host batches (H2D inside the timed
+           region, loss read back every step).  Also reported: the hash-encode kernel's achieved GB/s vs the
+           measured HBM peak (roofline), full-frame render Mpix/s (config 2), the oracle on the host cores
+           (cpu_baseline) and the reference's eager torch path on this GPU.
+reference  the reference's algorithm (oracle port: the Python reference cannot travel to the GPU box) on the
+           host cores, same metric/unit, bounded sample of the workload per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS_PER_RANK = 65536
+N_SAMPLES, N_IMPORTANCE = 64, 128
+HASH_BYTES_PER_POINT = 12 + 16 * 8 * 2 * 4 + 16 * 2 * 4      # 1164 B/point
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return dist.get_rank(), world, local
+    return 0, 1, 0
+
+
+def max_over_ranks(ms, world):
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def time_steps(fn, steps, world):
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+def cpu_reference_steps(steps, warmup, rays_per_step, threads):
+    """The oracle's train step on the host cores.  Returns (rays_per_s, ms_per_step)."""
+    from indoor_nerf_b200 import synthetic
+    from oracle.train_step import OracleModel, train_step
+    torch.set_num_threads(threads)
+    scene = synthetic.blender_scene(400, 400, n_views=100)
+    model = OracleModel(*scene["bounding_box"], log2T=19, finest=512, device="cpu", lr=0.01)
+    batches = [synthetic.ray_batch(scene, rays_per_step, seed=100 + i) for i in range(2)]
+    for i in range(warmup):
+        train_step(model, *batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        train_step(model, *batches[i % 2])
+    dt = time.perf_counter() - t0
+    return rays_per_step * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    rays = 1024 if total <= 16 else (256 if total <= 64 else 64)
+    v, ms = cpu_reference_steps(args.steps, args.warmup, rays, threads)
+    line = {
+        "impl": "reference", "metric": "train_rays_per_s", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": "%d rays/step of the 65536-ray workload (64+128 samples, T=2^19), full train step "
+                                   "(render fwd, img+sparsity+TV losses, backward, RAdam) by the oracle on the host" % rays},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    return {"workload": "BASELINE configs[2]: chair-shaped synthetic Blender scene 400x400, HashNeRF training step, "
+                        "N_rand=65536 rays per GPU, 64 coarse + 128 importance samples, 16 levels, log2_hashmap 19, "
+                        "finest_res 512, NeRFSmall coarse+fine, white_bkgd, perturb=1",
+            "rays_per_gpu": RAYS_PER_RANK, "global_rays_per_step": RAYS_PER_RANK * n,
+            "points_per_ray": 2 * N_SAMPLES + N_IMPORTANCE, "parallelism": "dp%d" % n,
+            "l2_policy": "inputs larger than L2: 16.8 M points/step (201 MB positions, 2.1 GB features) stream "
+                         "through; the 64 MiB table set is L2-resident by design"}
+
+
+def run_ours(args):
+    import indoor_nerf_b200 as pn
+    from indoor_nerf_b200 import _lib, model as pmodel, ops, synthetic
+    from indoor_nerf_b200.trainer import Trainer
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(1234 + rank)
+    scene = synthetic.blender_scene(400, 400, n_views=100)
+    a = pmodel.default_args(bounding_box=scene["bounding_box"], lrate=0.01)
+    torch.manual_seed(0)                                   # identical initial parameters on every rank
+    kw_train, kw_test, _, _, opt = pmodel.create_nerf(a, device=dev)
+    torch.manual_seed(1234 + rank)
+    tr = Trainer(a, kw_train, opt, scene["H"], scene["W"], scene["K"], scene["near"], scene["far"],
+                 group=None if world == 1 else torch.distributed.group.WORLD)
+    pool = [synthetic.ray_batch(scene, RAYS_PER_RANK, seed=1000 * rank + i, pin=True) for i in range(4)]
+    pool_dev = [(r.to(dev), t.to(dev)) for r, t in pool]
+    h2d = pool[0][0].numel() * 4 + pool[0][1].numel() * 4
+
+    def step_resident(i):
+        r, t = pool_dev[i % len(pool_dev)]
+        tr.step(r, t)
+
+    losses = []
+
+    def step_e2e(i):
+        r, t = pool[i % len(pool)]
+        loss, _ = tr.step(r.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
+        losses.append(loss.item())
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    with ClockSampler(local) as clk:
+        l0 = _lib.launch_count()
+        ms = time_steps(step_resident, args.steps, world)
+        launches = _lib.launch_count() - l0
+        ms_e2e = time_steps(step_e2e, args.steps, world)
+    rays_total = RAYS_PER_RANK * world * args.steps
+    value = rays_total / (ms / 1e3)
+    e2e = rays_total / (ms_e2e / 1e3)
+
+    line = {
+        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "final_loss": losses[-1] if losses else None,
+    }
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel: hash-encode forward on the fine pass's point set ---------
+        embed = kw_train["embed_fn"]
+        P = RAYS_PER_RANK * (N_SAMPLES + N_IMPORTANCE)
+        r, t = pool_dev[0]
+        with torch.no_grad():
+            z = torch.sort(2.0 + 4.0 * torch.rand(RAYS_PER_RANK, N_SAMPLES + N_IMPORTANCE, device=dev), -1)[0]
+            pts = ops.make_points(r[0], r[1], z).reshape(-1, 3)
+            tables = [tt.detach() for tt in embed.tables()]
+            for _ in range(3):
+                ops.hash_encode_fwd(embed.grid(), tables, pts)
+            reps = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                ops.hash_encode_fwd(embed.grid(), tables, pts)
+            e1.record()
+            torch.cuda.synchronize()
+            t_fwd = e0.elapsed_time(e1) / reps
+            dfeat = torch.randn(P, 32, device=dev)
+            flat = torch.zeros(16, 1 << 19, 2, device=dev)
+            for _ in range(2):
+                ops.hash_encode_bwd(embed.grid(), list(flat.unbind(0)), pts, dfeat)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                ops.hash_encode_bwd(embed.grid(), list(flat.unbind(0)), pts, dfeat)
+            e1.record()
+            torch.cuda.synchronize()
+            t_bwd = e0.elapsed_time(e1) / reps
+            del dfeat, flat, pts, z
+        peak, how = peaks()
+        ach = HASH_BYTES_PER_POINT * P / (t_fwd * 1e-3) / 1e9
+        line["roofline"] = {"kernel": "hash_fwd_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": None, "peak_source": how,
+                            "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT, "points_per_launch": P,
+                            "ms_per_launch": t_fwd,
+                            "backward": {"kernel": "hash_bwd_kernel", "ms_per_launch": t_bwd,
+                                         "achieved": HASH_BYTES_PER_POINT * P / (t_bwd * 1e-3) / 1e9}}
+        # ---- config 2: full 800x800 test-view render, finest_res 1024 -----------------------------------
+        try:
+            scene2 = synthetic.blender_scene(800, 800, n_views=8)
+            a2 = pmodel.default_args(bounding_box=scene2["bounding_box"], finest_res=1024)
+            _, kw2, _, _, _ = pmodel.create_nerf(a2, device=dev)
+            c2w = torch.from_numpy(scene2["poses"][0][:3, :4])
+            def frame():
+                with torch.no_grad():
+                    return pn.render(800, 800, scene2["K"], chunk=1 << 17, c2w=c2w, near=2., far=6., **kw2)
+            frame(); frame()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                frame()
+            e1.record()
+            torch.cuda.synchronize()
+            t_frame = e0.elapsed_time(e1) / 3
+            line["render"] = {"workload": "BASELINE configs[1]: 800x800 test view, finest_res 1024, 64+128 samples",
+                              "mpix_per_s": 0.64 / (t_frame * 1e-3), "ms_per_frame": t_frame}
+            del kw2
+        except Exception as ex:                                     # keep the headline even if this leg fails
+            line["render"] = {"error": repr(ex)}
+        torch.cuda.empty_cache()
+        if world == 1 and not args.no_baselines:
+            # ---- reference eager path on this GPU (the oracle's ATen ops), for the >=50x target ------------
+            try:
+                from oracle.train_step import OracleModel, train_step
+                om = OracleModel(*scene["bounding_box"], log2T=19, finest=512, device=dev, lr=0.01)
+                r, t = pool_dev[0]
+                train_step(om, r, t)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    train_step(om, r, t)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / 2
+                line["reference_eager_b200"] = {"value": RAYS_PER_RANK / dt, "unit": "rays/s", "ms_per_step": dt * 1e3,
+                                                "what": "oracle (the reference's eager ATen op sequence) on the same "
+                                                        "B200, same 65536-ray step, chunk 32768"}
+                del om
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                line["reference_eager_b200"] = {"error": repr(ex)}
+            # ---- oracle on the host cores -----------------------------------------------------------------------
+            threads = os.cpu_count() or 1
+            v, msc = cpu_reference_steps(3, 1, 1024, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "ms_per_step": msc,
+                                    "sample": "1024 rays/step of the same workload (64+128 samples, T=2^19), full "
+                                              "train step by the oracle, 1 warm-up + 3 timed steps"}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-baselines", action="store_true", help="skip the CPU / eager-GPU baseline legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,212 @@
+/*
+ * pocketnerf.h — C ABI of libpocketnerf.so: the B200 (sm_100a) implementation of PocketNeRF's
+ * HashNeRF hot path  HashEmbedder -> SHEncoder -> NeRFSmall -> raw2outputs -> sample_pdf.
+ *
+ * The reference (ryanjsuh/indoor-nerf, PocketNeRF/) is pure Python on PyTorch and has no FFI of
+ * its own; the "operator API" a replacement must serve is the set of Python callables named in
+ * SURVEY.md §8b.  Each entry point below states the reference lines whose arithmetic it replaces
+ * (paths relative to PocketNeRF/).  The Python host layer (indoor-nerf_b200/) binds these with
+ * ctypes and re-exports the reference's names; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every pointer marked "device" is caller-owned device memory on the CURRENT device; the library
+ *    never allocates, frees or synchronises (exceptions are noted); pointers marked "host" are read
+ *    during the call only.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *  - return 0 on success, a negative PN_E* code otherwise; pn_last_error() (thread-local) says why.
+ *  - floats are IEEE fp32; where the reference's result is an integer (hash indices, sample bins)
+ *    or a fixed sequence of individually rounded fp32 ops (voxel weights, trilinear interpolation,
+ *    SH, fake-quant, o+d*z), the kernels reproduce it bit for bit (no FMA contraction there).
+ *  - no entry point has a CPU implementation: without a CUDA device they fail with PN_ECUDA.
+ */
+#ifndef POCKETNERF_H
+#define POCKETNERF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN_ABI_VERSION 3
+#define PN_MAX_LEVELS 16
+
+#define PN_EINVAL (-1)   /* bad argument */
+#define PN_ECUDA  (-2)   /* CUDA runtime error (launch failure, no device, ...) */
+#define PN_ESHAPE (-3)   /* shape outside what the kernels are built for */
+
+typedef void *pn_stream_t; /* cudaStream_t */
+
+int pn_abi_version(void);
+const char *pn_last_error(void);
+/* Number of kernels this library has launched since load (all threads); bench.py's gpu_launches. */
+int64_t pn_launch_count(void);
+
+/* ---- hash grid ---------------------------------------------------------------------------- */
+
+/* Geometry of the multiresolution hash grid; replaces the per-call tensor arithmetic of
+ * HashEmbedder.forward (hash_encoding.py:82-107) and get_voxel_vertices (utils.py:95-117).
+ * `resolution[l]` must be the value of torch.floor(base_resolution * b**l) evaluated with the
+ * reference's own float32 expression (hash_encoding.py:28,89) — the host layer does that. */
+typedef struct {
+  float box_min[3];
+  float box_max[3];
+  float resolution[PN_MAX_LEVELS];
+  int32_t n_levels;          /* 1..16 */
+  int32_t log2_hashmap_size; /* 1..30; table l has 2^log2_hashmap_size rows of 2 floats */
+} pn_hash_grid;
+
+/* Per-level fake-quant of the gathered corner embeddings (hash_encoding.py:97-101 calling
+ * LearnedBitwidthQuantizer.forward, quantization.py:144-187).  One row of 8 floats per level in
+ * DEVICE memory so that no host sync is needed when soft_bits move:
+ *   [0] scale  [1] scale+1e-8 (the divisor)  [2] zero_point  [3] qmin  [4] qmax
+ *   [5] enabled (0/1)  [6] mode: 1 = training form x+(dq-x), 0 = eval form dq  [7] unused */
+#define PN_QROW 8
+
+/* feat[P, 2*n_levels], keep[P] (1 = inside the box on all three axes) from points x[P,3].
+ *   tables: host array of n_levels device pointers (the reference's nn.Embedding weights [T,2]).
+ *   qparams: device [n_levels][PN_QROW] or NULL.   Reference: hash_encoding.py:82-107. */
+int pn_hash_encode_fwd(const pn_hash_grid *grid, const float *const *tables, const float *qparams,
+                       const float *x, int64_t n_points, float *feat, uint8_t *keep,
+                       pn_stream_t stream);
+
+/* dtables[l][h] += sum over points/corners of the trilinear weight times dfeat — the dense
+ * gradient aten::embedding_dense_backward gives the reference (hash_encoding.py:94 under
+ * autograd).  Accumulates (atomics) into caller-zeroed dtables; the fake-quant is a
+ * straight-through estimator, so it does not appear here. */
+int pn_hash_encode_bwd(const pn_hash_grid *grid, float *const *dtables, const float *x,
+                       const float *dfeat, int64_t n_points, pn_stream_t stream);
+
+/* The 8 hashed corner indices per level, idx[P, n_levels, 8] (int32) in the reference's corner
+ * order (utils.py:9, 13-24, 114-115).  Test/diagnostic entry for the bit-exact index claim. */
+int pn_hash_indices(const pn_hash_grid *grid, const float *x, int64_t n_points, int32_t *idx,
+                    pn_stream_t stream);
+
+/* utils.hash (utils.py:13-24) on int64 coordinates coords[n, dim], dim <= 3 — used by the TV loss
+ * (loss.py:29).  out[n] int64. */
+int pn_hash_coords(const int64_t *coords, int64_t n, int dim, int log2_hashmap_size, int64_t *out,
+                   pn_stream_t stream);
+
+/* Per-level min and max of the gathered corner values, minmax[n_levels][2] (caller initialises
+ * to +inf/-inf) — the batch statistics LearnedBitwidthQuantizer.calibrate reads
+ * (quantization.py:97-119) on the first quantised training call. */
+int pn_hash_gather_minmax(const pn_hash_grid *grid, const float *const *tables, const float *x,
+                          int64_t n_points, float *minmax, pn_stream_t stream);
+
+/* ---- view-direction encoding ---------------------------------------------------------------- */
+
+/* out[n,16] = degree-4 real spherical harmonics of dirs[n,3] (hash_encoding.py:153-191). */
+int pn_sh_encode(const float *dirs, int64_t n, float *out, pn_stream_t stream);
+
+/* ---- NeRFSmall ---------------------------------------------------------------------------------- */
+
+/* Weights in the reference's nn.Linear layout [out,in], row-major (run_nerf_helpers.py:187-263 with
+ * the create_nerf shapes, run_nerf.py:240-247): s0[64,32] s1[16,64] c0[64,31] c1[64,64] c2[3,64];
+ * optional normal head n0w[32,15] n0b[32] n2w[3,32] n2b[3] (all four NULL when absent). */
+typedef struct {
+  const float *s0, *s1, *c0, *c1, *c2;
+  const float *n0w, *n0b, *n2w, *n2b;
+} pn_mlp_weights;
+
+typedef struct {
+  float *s0, *s1, *c0, *c1, *c2;
+  float *n0w, *n0b, *n2w, *n2b;
+} pn_mlp_grads;
+
+/* Inputs of one NeRFSmall evaluation over n_points rows.
+ *   feat   device [n_points, 32], row stride feat_stride floats.
+ *   view   either sh (device [n_points,16], row stride sh_stride) or dirs (device [n_rays,3]) with
+ *          samples_per_ray: point p uses dirs[p / samples_per_ray] and the SH basis is evaluated in
+ *          the kernel (run_nerf.py:59-63 + hash_encoding.py:153-191).  Exactly one is non-NULL.
+ *   act_q  device [PN_QROW] fake-quant of the hidden activation after the first ReLU
+ *          (run_nerf_helpers.py:281-284) or NULL.
+ *   keep   device [n_points] or NULL; where 0 the LAST output channel is set to 0 and receives no
+ *          gradient (run_nerf.py:66 — sigma for 4 channels, normal_z for 7, as the reference does). */
+typedef struct {
+  const float *feat;
+  int64_t feat_stride;
+  const float *sh;
+  int64_t sh_stride;
+  const float *dirs;
+  int32_t samples_per_ray;
+  const float *act_q;
+  const uint8_t *keep;
+  int64_t n_points;
+} pn_mlp_input;
+
+/* out[n_points, 4] = (r,g,b,sigma) or [n_points,7] with the normalised normal appended when the
+ * normal head is present (run_nerf_helpers.py:265-306). */
+int pn_mlp_fwd(const pn_mlp_weights *w, const pn_mlp_input *in, float *out, pn_stream_t stream);
+
+/* Backward of pn_mlp_fwd for the cotangent dout[n_points, 4|7]:
+ *   dfeat [n_points,32] (stride dfeat_stride) written; dsh [n_points,16] written when non-NULL (only
+ *   valid with in->sh); dw accumulated (atomics) into caller-zeroed buffers. */
+int pn_mlp_bwd(const pn_mlp_weights *w, const pn_mlp_input *in, const float *dout, float *dfeat,
+               int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads *dw,
+               pn_stream_t stream);
+
+/* ---- volume rendering ---------------------------------------------------------------------------- */
+
+/* raw2outputs (run_nerf.py:347-411).  raw[N,S,C] C = 4 or 7, z[N,S], rays_d[N,3], noise[N,S] or NULL
+ * (already multiplied by raw_noise_std).  Outputs: rgb[N,3] disp[N] acc[N] weights[N,S] depth[N]
+ * sparsity[N] normal[N,3] (normal only when C == 7 and non-NULL). S <= 512. */
+int pn_composite_fwd(const float *raw, int channels, const float *z, const float *rays_d,
+                     const float *noise, int64_t n_rays, int n_samples, int white_bkgd, float *rgb,
+                     float *disp, float *acc, float *weights, float *depth, float *sparsity,
+                     float *normal, pn_stream_t stream);
+
+/* Backward of pn_composite_fwd.  Any cotangent pointer may be NULL (treated as zeros).
+ * draw[N,S,C] is written (not accumulated). */
+int pn_composite_bwd(const float *raw, int channels, const float *z, const float *rays_d,
+                     const float *noise, int64_t n_rays, int n_samples, int white_bkgd,
+                     const float *d_rgb, const float *d_disp, const float *d_acc,
+                     const float *d_weights, const float *d_depth, const float *d_sparsity,
+                     const float *d_normal, float *draw, pn_stream_t stream);
+
+/* sample_pdf (run_nerf_helpers.py:354-397).  bins[N,nb], weights: nb-1 values per ray starting at
+ * weights + r*w_stride; u: row r at u + r*u_stride (u_stride = 0 broadcasts one row, which is how
+ * the host passes torch.linspace(0,1,M) for det=True).  samples[N,M]; inds[N,M] (int32, the
+ * searchsorted(right=True) result) and cdf[N,nb] are optional outputs.  nb <= 512. */
+int pn_sample_pdf(const float *bins, const float *weights, int64_t w_stride, const float *u,
+                  int64_t u_stride, int64_t n_rays, int nb, int n_samples, float *samples,
+                  int32_t *inds, float *cdf, pn_stream_t stream);
+
+/* The inversion step alone, from a caller-supplied cdf[N,nb] (run_nerf_helpers.py:381-397): the
+ * entry whose bin indices are bit-exact by construction. */
+int pn_sample_from_cdf(const float *cdf, const float *bins, const float *u, int64_t u_stride,
+                       int64_t n_rays, int nb, int n_samples, float *samples, int32_t *inds,
+                       pn_stream_t stream);
+
+/* out[N, sa+sb] = ascending sort of the concatenation of a[N,sa] and b[N,sb]
+ * (torch.sort(torch.cat(...)) at run_nerf.py:512).  sa+sb <= 512. */
+int pn_sort_merge(const float *a, int sa, const float *b, int sb, int64_t n_rays, float *out,
+                  pn_stream_t stream);
+
+/* ---- rays ------------------------------------------------------------------------------------------ */
+
+/* get_rays (run_nerf_helpers.py:311-320): K host[9] row-major intrinsics, c2w host[12] row-major
+ * [3,4]; rays_o, rays_d device [H,W,3]. */
+int pn_gen_rays(int height, int width, const float *K, const float *c2w, float *rays_o,
+                float *rays_d, pn_stream_t stream);
+
+/* ndc_rays (run_nerf_helpers.py:333-350) on n rays: rays_o/rays_d device [n,3] -> out_o/out_d [n,3].
+ * focal and near are host scalars (python floats in the reference). */
+int pn_ndc_rays(int height, int width, double focal, double near, const float *rays_o,
+                const float *rays_d, int64_t n, float *out_o, float *out_d, pn_stream_t stream);
+
+/* pts[N,S,3] = rays_o[N,3] + rays_d[N,3] * z[N,S]  (run_nerf.py:490,513), mul then add, each
+ * rounded.  o_stride/d_stride are the row strides (in floats) of rays_o / rays_d. */
+int pn_make_points(const float *rays_o, int64_t o_stride, const float *rays_d, int64_t d_stride,
+                   const float *z, int64_t n_rays, int n_samples, float *pts, pn_stream_t stream);
+
+/* Stratified coarse depths (run_nerf.py:466-488): z[N,S] from near[N], far[N] (row stride
+ * nf_stride floats each), t_vals[S] (the host passes torch.linspace(0,1,S) so that its rounding
+ * is the reference's), optional t_rand[N,S] (NULL = no perturbation), lindisp flag. */
+int pn_coarse_z(const float *near, const float *far, int64_t nf_stride, const float *t_vals,
+                const float *t_rand, int64_t n_rays, int n_samples, int lindisp, float *z,
+                pn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POCKETNERF_H */

@@ -1,0 +1,144 @@
+// Per-point arithmetic of the multiresolution hash grid, written once as host/device functions so
+// that the kernels (hash_encode.cu, later the fused field kernels) and the test-only host emulation
+// (tests/hostemu) execute the same source.
+//
+// Reference arithmetic, in the reference's op order (every op individually rounded):
+//   utils.py:95-117   keep = x == max(min(x, bmax), bmin);  xc = clamp(x, bmin, bmax)
+//                     g = (bmax - bmin) / res;  i = floor((xc - bmin) / g)
+//                     vmin = i*g + bmin;  vmax = vmin + g
+//   utils.py:13-24    h = (cx*1) ^ (cy*2654435761) ^ (cz*805459861)  & (2^T - 1)   [int64 in torch;
+//                     the low T<=30 bits are those of the uint32-wrapped product, which is what we do]
+//   hash_encoding.py:64   w = (x - vmin) / (vmax - vmin)      with the UNclamped x (:103)
+//   hash_encoding.py:68-78  lerp along x (corner pairs c, c+4), then y, then z
+#pragma once
+#include "pn_common.cuh"
+
+namespace pn {
+
+struct HashGridDev {
+  float bmin[3];
+  float bmax[3];
+  float g[PN_MAX_LEVELS][3];   // (bmax - bmin) / res[l], IEEE fp32, computed once on the host
+  int n_levels;
+  uint32_t mask;
+};
+
+// utils.py:107  grid_size = (box_max - box_min) / resolution
+inline HashGridDev make_grid_dev(const pn_hash_grid &h) {
+  HashGridDev G;
+  for (int a = 0; a < 3; ++a) { G.bmin[a] = h.box_min[a]; G.bmax[a] = h.box_max[a]; }
+  for (int l = 0; l < PN_MAX_LEVELS; ++l)
+    for (int a = 0; a < 3; ++a)
+      G.g[l][a] = (l < h.n_levels) ? pn_div(pn_sub(h.box_max[a], h.box_min[a]), h.resolution[l]) : 1.0f;
+  G.n_levels = h.n_levels;
+  G.mask = (1u << h.log2_hashmap_size) - 1u;
+  return G;
+}
+
+#define PN_PRIME_Y 2654435761u
+#define PN_PRIME_Z 805459861u
+
+struct Cell {
+  uint32_t hx0, hx1;   // ix, ix+1           (prime 1)
+  uint32_t hy0, hy1;   // iy*P_Y, (iy+1)*P_Y
+  uint32_t hz0, hz1;   // iz*P_Z, (iz+1)*P_Z
+  float w[3];          // trilinear weights (may leave [0,1] for points outside the box)
+};
+
+// keep flag of one point: inside (inclusive) the box on all axes; NaN -> not kept.
+PN_HD bool point_keep(const HashGridDev &G, const float x[3]) {
+  bool k = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float c = fmaxf(fminf(x[a], G.bmax[a]), G.bmin[a]);
+    k = k && (x[a] == c);
+  }
+  return k;
+}
+
+PN_HD void point_cell(const HashGridDev &G, int level, const float x[3], Cell &c) {
+  uint32_t ii[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float g = G.g[level][a];
+    // torch.clamp(x, min, max) == min(max(x, lo), hi)
+    const float xc = fminf(fmaxf(x[a], G.bmin[a]), G.bmax[a]);
+    const float fi = floorf(pn_div(pn_sub(xc, G.bmin[a]), g));
+    const int i = (int)fi;                                   // .int() : fi is integral, >= 0
+    const float vmin = pn_add(pn_mul((float)i, g), G.bmin[a]);
+    const float vmax = pn_add(vmin, g);                      // 1.0*g == g exactly
+    c.w[a] = pn_div(pn_sub(x[a], vmin), pn_sub(vmax, vmin));
+    ii[a] = (uint32_t)i;
+  }
+  c.hx0 = ii[0];
+  c.hx1 = ii[0] + 1u;
+  c.hy0 = ii[1] * PN_PRIME_Y;
+  c.hy1 = c.hy0 + PN_PRIME_Y;
+  c.hz0 = ii[2] * PN_PRIME_Z;
+  c.hz1 = c.hz0 + PN_PRIME_Z;
+}
+
+// corner id = 4*dx + 2*dy + dz   (utils.py:9)
+PN_HD uint32_t corner_index(const HashGridDev &G, const Cell &c, int corner) {
+  const uint32_t hx = (corner & 4) ? c.hx1 : c.hx0;
+  const uint32_t hy = (corner & 2) ? c.hy1 : c.hy0;
+  const uint32_t hz = (corner & 1) ? c.hz1 : c.hz0;
+  return (hx ^ hy ^ hz) & G.mask;
+}
+
+// LearnedBitwidthQuantizer.forward on one value (quantization.py:177-187); q = row of PN_QROW floats.
+PN_HD float fake_quant(float x, float scale, float denom, float zp, float qmin, float qmax, bool train_form) {
+  float q = rintf(pn_add(pn_div(x, denom), zp));             // torch.round = half to even
+  q = fminf(fmaxf(q, qmin), qmax);
+  const float dq = pn_mul(pn_sub(q, zp), scale);
+  return train_form ? pn_add(x, pn_sub(dq, x)) : dq;
+}
+
+// hash_encoding.py:68-78 for one feature channel; e[corner].
+PN_HD float trilerp(const float e[8], const float w[3]) {
+  const float wx = w[0], wy = w[1], wz = w[2];
+  const float ox = pn_sub(1.0f, wx), oy = pn_sub(1.0f, wy), oz = pn_sub(1.0f, wz);
+  const float c00 = pn_add(pn_mul(e[0], ox), pn_mul(e[4], wx));
+  const float c01 = pn_add(pn_mul(e[1], ox), pn_mul(e[5], wx));
+  const float c10 = pn_add(pn_mul(e[2], ox), pn_mul(e[6], wx));
+  const float c11 = pn_add(pn_mul(e[3], ox), pn_mul(e[7], wx));
+  const float c0 = pn_add(pn_mul(c00, oy), pn_mul(c10, wy));
+  const float c1 = pn_add(pn_mul(c01, oy), pn_mul(c11, wy));
+  return pn_add(pn_mul(c0, oz), pn_mul(c1, wz));
+}
+
+// d(trilerp)/d(e[corner]) in autograd's multiplication order: ((g*wz')*wy')*wx'.
+PN_HD float corner_weight_times(float g, const float w[3], int corner) {
+  const float fz = (corner & 1) ? w[2] : pn_sub(1.0f, w[2]);
+  const float fy = (corner & 2) ? w[1] : pn_sub(1.0f, w[1]);
+  const float fx = (corner & 4) ? w[0] : pn_sub(1.0f, w[0]);
+  return pn_mul(pn_mul(pn_mul(g, fz), fy), fx);
+}
+
+// Degree-4 real SH (hash_encoding.py:153-191), python-float constants rounded to fp32 where torch
+// multiplies a tensor by a python scalar.
+PN_HD void sh4(float x, float y, float z, float o[16]) {
+  const float C1 = (float)(0.4886025119029199);
+  const float xx = pn_mul(x, x), yy = pn_mul(y, y), zz = pn_mul(z, z);
+  const float xy = pn_mul(x, y), yz = pn_mul(y, z), xz = pn_mul(x, z);
+  o[0] = (float)(0.28209479177387814);
+  o[1] = pn_mul(-C1, y);
+  o[2] = pn_mul(C1, z);
+  o[3] = pn_mul(-C1, x);
+  o[4] = pn_mul((float)(1.0925484305920792), xy);
+  o[5] = pn_mul((float)(-1.0925484305920792), yz);
+  o[6] = pn_mul((float)(0.31539156525252005), pn_sub(pn_sub(pn_mul(2.0f, zz), xx), yy));
+  o[7] = pn_mul((float)(-1.0925484305920792), xz);
+  o[8] = pn_mul((float)(0.5462742152960396), pn_sub(xx, yy));
+  o[9] = pn_mul(pn_mul((float)(-0.5900435899266435), y), pn_sub(pn_mul(3.0f, xx), yy));
+  o[10] = pn_mul(pn_mul((float)(2.890611442640554), xy), z);
+  const float t4 = pn_sub(pn_sub(pn_mul(4.0f, zz), xx), yy);
+  o[11] = pn_mul(pn_mul((float)(-0.4570457994644658), y), t4);
+  o[12] = pn_mul(pn_mul((float)(0.3731763325901154), z),
+                 pn_sub(pn_sub(pn_mul(2.0f, zz), pn_mul(3.0f, xx)), pn_mul(3.0f, yy)));
+  o[13] = pn_mul(pn_mul((float)(-0.4570457994644658), x), t4);
+  o[14] = pn_mul(pn_mul((float)(1.445305721320277), z), pn_sub(xx, yy));
+  o[15] = pn_mul(pn_mul((float)(-0.5900435899266435), x), pn_sub(xx, pn_mul(3.0f, yy)));
+}
+
+}  // namespace pn

@@ -1,0 +1,306 @@
+// K1 / K1b — multiresolution hash-grid encoder, forward gather and backward scatter-add.
+// Replaces HashEmbedder.forward (hash_encoding.py:82-107), get_voxel_vertices (utils.py:95-117),
+// hash (utils.py:13-24) and, in backward, the 16 aten::embedding_dense_backward calls.
+//
+// Work decomposition (B200): one thread per point, levels in an unrolled loop.  A warp therefore
+// holds 32 consecutive points — consecutive samples of one ray in the render path — which share
+// voxels at the coarse levels (same-address lanes coalesce into one L1 wavefront) and walk the same
+// 4 MiB table at the same time at every level.  The 64 MiB (T=2^19) table set is L2-resident on a
+// 126 MB L2; the [P,32] output is staged through shared memory so that each warp writes whole
+// 128-byte lines.  HBM traffic per point is then the algorithmic minimum 12 B in + 128 B out.
+#include "hash_core.cuh"
+
+namespace pn {
+
+struct TablePtrs {
+  const float2 *t[PN_MAX_LEVELS];
+};
+struct GradPtrs {
+  float2 *t[PN_MAX_LEVELS];
+};
+
+constexpr int kHashThreads = 128;
+constexpr int kHashWarps = kHashThreads / 32;
+constexpr int kStagePitch = 33;   // 32 floats + 1: conflict-free column writes and row reads
+
+__device__ __forceinline__ void load_point(const float *__restrict__ x, int64_t p, float xv[3]) {
+  xv[0] = __ldg(x + 3 * p + 0);
+  xv[1] = __ldg(x + 3 * p + 1);
+  xv[2] = __ldg(x + 3 * p + 2);
+}
+
+template <bool QUANT>
+__global__ void __launch_bounds__(kHashThreads)
+hash_fwd_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ TablePtrs T, const float *__restrict__ qparams,
+                const float *__restrict__ x, int64_t P, float *__restrict__ feat,
+                uint8_t *__restrict__ keep) {
+  __shared__ float stage[kHashWarps][32 * kStagePitch];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int F = 2 * G.n_levels;
+  float *st = stage[warp];
+  for (int64_t base = ((int64_t)blockIdx.x * kHashWarps + warp) * 32; base < P;
+       base += (int64_t)gridDim.x * kHashThreads) {
+    const int64_t p = base + lane;
+    const bool valid = p < P;
+    float xv[3] = {0.f, 0.f, 0.f};
+    if (valid) load_point(x, p, xv);
+#pragma unroll 4
+    for (int l = 0; l < G.n_levels; ++l) {
+      Cell c;
+      point_cell(G, l, xv, c);
+      const float2 *__restrict__ tab = T.t[l];
+      float2 e[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = __ldg(tab + corner_index(G, c, k));
+      float e0[8], e1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { e0[k] = e[k].x; e1[k] = e[k].y; }
+      if (QUANT) {
+        const float *q = qparams + l * PN_QROW;
+        if (q[5] != 0.f) {
+          const float scale = q[0], denom = q[1], zp = q[2], qmin = q[3], qmax = q[4];
+          const bool train_form = q[6] != 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            e0[k] = fake_quant(e0[k], scale, denom, zp, qmin, qmax, train_form);
+            e1[k] = fake_quant(e1[k], scale, denom, zp, qmin, qmax, train_form);
+          }
+        }
+      }
+      st[lane * kStagePitch + 2 * l + 0] = trilerp(e0, c.w);
+      st[lane * kStagePitch + 2 * l + 1] = trilerp(e1, c.w);
+    }
+    if (valid && keep) keep[p] = point_keep(G, xv) ? 1 : 0;
+    __syncwarp();
+    // 32 rows x F floats -> global, whole lines per warp
+    const int64_t rows = (P - base) < 32 ? (P - base) : 32;
+    if (F == 32) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int i4 = it * 32 + lane, row = i4 >> 3, c4 = (i4 & 7) * 4;
+        if (row < rows) {
+          const float *s = st + row * kStagePitch + c4;
+          float4 v = make_float4(s[0], s[1], s[2], s[3]);
+          *reinterpret_cast<float4 *>(feat + (base + row) * 32 + c4) = v;
+        }
+      }
+    } else {
+      for (int i = lane; i < 32 * F; i += 32) {
+        const int row = i / F, col = i - row * F;
+        if (row < rows) feat[(base + row) * F + col] = st[row * kStagePitch + col];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kHashThreads)
+hash_bwd_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ GradPtrs D, const float *__restrict__ x,
+                const float *__restrict__ dfeat, int64_t P) {
+  __shared__ float stage[kHashWarps][32 * kStagePitch];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int F = 2 * G.n_levels;
+  float *st = stage[warp];
+  for (int64_t base = ((int64_t)blockIdx.x * kHashWarps + warp) * 32; base < P;
+       base += (int64_t)gridDim.x * kHashThreads) {
+    const int64_t p = base + lane;
+    const bool valid = p < P;
+    const int64_t rows = (P - base) < 32 ? (P - base) : 32;
+    // dfeat rows -> shared, whole lines per warp
+    for (int i = lane; i < 32 * F; i += 32) {
+      const int row = i / F, col = i - row * F;
+      st[row * kStagePitch + col] = (row < rows) ? __ldg(dfeat + (base + row) * F + col) : 0.f;
+    }
+    __syncwarp();
+    float xv[3] = {0.f, 0.f, 0.f};
+    if (valid) load_point(x, p, xv);
+    if (valid) {
+#pragma unroll 2
+      for (int l = 0; l < G.n_levels; ++l) {
+        const float g0 = st[lane * kStagePitch + 2 * l + 0];
+        const float g1 = st[lane * kStagePitch + 2 * l + 1];
+        if (g0 == 0.f && g1 == 0.f) continue;    // e.g. masked / zero-weight samples
+        Cell c;
+        point_cell(G, l, xv, c);
+        float2 *tab = D.t[l];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 v = make_float2(corner_weight_times(g0, c.w, k), corner_weight_times(g1, c.w, k));
+          atomicAdd(tab + corner_index(G, c, k), v);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void hash_indices_kernel(const __grid_constant__ HashGridDev G, const float *__restrict__ x, int64_t P,
+                                    int32_t *__restrict__ idx) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float xv[3];
+  load_point(x, p, xv);
+  for (int l = 0; l < G.n_levels; ++l) {
+    Cell c;
+    point_cell(G, l, xv, c);
+    for (int k = 0; k < 8; ++k) idx[(p * G.n_levels + l) * 8 + k] = (int32_t)corner_index(G, c, k);
+  }
+}
+
+__global__ void hash_coords_kernel(const int64_t *__restrict__ coords, int64_t n, int dim, uint32_t mask,
+                                   int64_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t primes[3] = {1u, PN_PRIME_Y, PN_PRIME_Z};
+  uint32_t h = 0;
+  for (int d = 0; d < dim; ++d) h ^= (uint32_t)coords[i * dim + d] * primes[d];
+  out[i] = (int64_t)(h & mask);
+}
+
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_float(float *addr, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(256)
+hash_minmax_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ TablePtrs T, const float *__restrict__ x, int64_t P,
+                   float *__restrict__ minmax) {
+  const int lane = threadIdx.x & 31;
+  float lo[PN_MAX_LEVELS], hi[PN_MAX_LEVELS];
+#pragma unroll
+  for (int l = 0; l < PN_MAX_LEVELS; ++l) { lo[l] = INFINITY; hi[l] = -INFINITY; }
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    float xv[3];
+    load_point(x, p, xv);
+#pragma unroll
+    for (int l = 0; l < PN_MAX_LEVELS; ++l) {
+      if (l < G.n_levels) {
+        Cell c;
+        point_cell(G, l, xv, c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 e = __ldg(T.t[l] + corner_index(G, c, k));
+          lo[l] = fminf(lo[l], fminf(e.x, e.y));
+          hi[l] = fmaxf(hi[l], fmaxf(e.x, e.y));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < PN_MAX_LEVELS; ++l) {
+    if (l < G.n_levels) {
+      float a = lo[l], b = hi[l];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+      }
+      if (lane == 0) {
+        if (a != INFINITY) atomic_min_float(minmax + 2 * l + 0, a);
+        if (b != -INFINITY) atomic_max_float(minmax + 2 * l + 1, b);
+      }
+    }
+  }
+}
+
+static int check_grid(const pn_hash_grid *g) {
+  PN_REQUIRE(g != nullptr, PN_EINVAL, "grid is NULL");
+  PN_REQUIRE(g->n_levels >= 1 && g->n_levels <= PN_MAX_LEVELS, PN_ESHAPE, "n_levels %d outside 1..%d",
+             g->n_levels, PN_MAX_LEVELS);
+  PN_REQUIRE(g->log2_hashmap_size >= 1 && g->log2_hashmap_size <= 30, PN_ESHAPE,
+             "log2_hashmap_size %d outside 1..30", g->log2_hashmap_size);
+  for (int l = 0; l < g->n_levels; ++l)
+    PN_REQUIRE(g->resolution[l] >= 1.f && g->resolution[l] < 1e6f, PN_EINVAL, "resolution[%d]=%g", l,
+               (double)g->resolution[l]);
+  return 0;
+}
+
+static int hash_blocks(int64_t P, int threads, int per_sm) {
+  const int64_t need = ceil_div(P, threads);
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int pn_hash_encode_fwd(const pn_hash_grid *grid, const float *const *tables, const float *qparams,
+                                  const float *x, int64_t n_points, float *feat, uint8_t *keep,
+                                  pn_stream_t stream) {
+  if (int e = check_grid(grid)) return e;
+  PN_REQUIRE(tables && x && feat, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(n_points >= 0, PN_EINVAL, "n_points < 0");
+  if (n_points == 0) return 0;
+  const HashGridDev G = make_grid_dev(*grid);
+  TablePtrs T;
+  for (int l = 0; l < PN_MAX_LEVELS; ++l)
+    T.t[l] = reinterpret_cast<const float2 *>(tables[l < grid->n_levels ? l : 0]);
+  for (int l = 0; l < grid->n_levels; ++l) PN_REQUIRE(tables[l] != nullptr, PN_EINVAL, "tables[%d] is NULL", l);
+  const int blocks = hash_blocks(n_points, kHashThreads, 16);
+  if (qparams)
+    hash_fwd_kernel<true><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, qparams, x, n_points, feat, keep);
+  else
+    hash_fwd_kernel<false><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, nullptr, x, n_points, feat, keep);
+  count_launch();
+  return check_launch("hash_fwd_kernel");
+}
+
+extern "C" int pn_hash_encode_bwd(const pn_hash_grid *grid, float *const *dtables, const float *x,
+                                  const float *dfeat, int64_t n_points, pn_stream_t stream) {
+  if (int e = check_grid(grid)) return e;
+  PN_REQUIRE(dtables && x && dfeat, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(n_points >= 0, PN_EINVAL, "n_points < 0");
+  if (n_points == 0) return 0;
+  const HashGridDev G = make_grid_dev(*grid);
+  GradPtrs D;
+  for (int l = 0; l < PN_MAX_LEVELS; ++l) D.t[l] = reinterpret_cast<float2 *>(dtables[l < grid->n_levels ? l : 0]);
+  for (int l = 0; l < grid->n_levels; ++l) PN_REQUIRE(dtables[l] != nullptr, PN_EINVAL, "dtables[%d] is NULL", l);
+  const int blocks = hash_blocks(n_points, kHashThreads, 16);
+  hash_bwd_kernel<<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, D, x, dfeat, n_points);
+  count_launch();
+  return check_launch("hash_bwd_kernel");
+}
+
+extern "C" int pn_hash_indices(const pn_hash_grid *grid, const float *x, int64_t n_points, int32_t *idx,
+                               pn_stream_t stream) {
+  if (int e = check_grid(grid)) return e;
+  PN_REQUIRE(x && idx, PN_EINVAL, "NULL pointer argument");
+  if (n_points <= 0) return 0;
+  const HashGridDev G = make_grid_dev(*grid);
+  hash_indices_kernel<<<(unsigned)ceil_div(n_points, 128), 128, 0, as_stream(stream)>>>(G, x, n_points, idx);
+  count_launch();
+  return check_launch("hash_indices_kernel");
+}
+
+extern "C" int pn_hash_coords(const int64_t *coords, int64_t n, int dim, int log2_hashmap_size, int64_t *out,
+                              pn_stream_t stream) {
+  PN_REQUIRE(coords && out, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(dim >= 1 && dim <= 3, PN_ESHAPE, "dim %d outside 1..3", dim);
+  PN_REQUIRE(log2_hashmap_size >= 1 && log2_hashmap_size <= 30, PN_ESHAPE, "log2_hashmap_size %d",
+             log2_hashmap_size);
+  if (n <= 0) return 0;
+  hash_coords_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+      coords, n, dim, (1u << log2_hashmap_size) - 1u, out);
+  count_launch();
+  return check_launch("hash_coords_kernel");
+}
+
+extern "C" int pn_hash_gather_minmax(const pn_hash_grid *grid, const float *const *tables, const float *x,
+                                     int64_t n_points, float *minmax, pn_stream_t stream) {
+  if (int e = check_grid(grid)) return e;
+  PN_REQUIRE(tables && x && minmax, PN_EINVAL, "NULL pointer argument");
+  if (n_points <= 0) return 0;
+  const HashGridDev G = make_grid_dev(*grid);
+  TablePtrs T;
+  for (int l = 0; l < PN_MAX_LEVELS; ++l)
+    T.t[l] = reinterpret_cast<const float2 *>(tables[l < grid->n_levels ? l : 0]);
+  const int blocks = hash_blocks(n_points, 256, 4);
+  hash_minmax_kernel<<<blocks, 256, 0, as_stream(stream)>>>(G, T, x, n_points, minmax);
+  count_launch();
+  return check_launch("hash_minmax_kernel");
+}

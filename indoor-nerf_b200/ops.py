@@ -1,0 +1,404 @@
+"""Operator layer: thin, typed wrappers over the C ABI plus the autograd formulas that tie the
+forward and backward kernels together.  Nothing here computes on the CPU or falls back to torch ops for
+the hot path; torch allocates the outputs and provides the stream."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import HashGrid, MlpInput, MlpWeights, call, dptr, fcontig, stream
+
+_MLP_KEYS = ("s0", "s1", "c0", "c1", "c2", "n0w", "n0b", "n2w", "n2b")
+
+
+def _guard(t):
+    if not t.is_cuda:
+        raise _lib.PocketNerfError("expected a CUDA tensor, got device %s — there is no CPU path" % t.device)
+    return torch.cuda.device(t.device)
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * _lib.MAX_LEVELS)(*[t.data_ptr() for t in tensors])
+
+
+# ---------------------------------------------------------------------------------------------------
+# hash grid
+# ---------------------------------------------------------------------------------------------------
+def make_grid(box_min, box_max, resolutions, log2_hashmap_size):
+    g = HashGrid()
+    g.box_min[:] = [float(v) for v in box_min]
+    g.box_max[:] = [float(v) for v in box_max]
+    res = [float(r) for r in resolutions]
+    if not 1 <= len(res) <= _lib.MAX_LEVELS:
+        raise _lib.PocketNerfError("n_levels %d outside 1..%d" % (len(res), _lib.MAX_LEVELS))
+    g.resolution[:len(res)] = res
+    g.n_levels = len(res)
+    g.log2_hashmap_size = int(log2_hashmap_size)
+    return g
+
+
+def _check_tables(grid, tables):
+    rows = 1 << grid.log2_hashmap_size
+    if len(tables) != grid.n_levels:
+        raise _lib.PocketNerfError("expected %d tables, got %d" % (grid.n_levels, len(tables)))
+    for t in tables:
+        if tuple(t.shape) != (rows, 2):
+            raise _lib.PocketNerfError("table shape %s != (%d, 2)" % (tuple(t.shape), rows))
+        dptr(t)
+
+
+def hash_encode_fwd(grid, tables, x, qparams=None):
+    """x[P,3] -> feat[P,2L], keep[P] (bool).   Reference: hash_encoding.py:82-107."""
+    x = fcontig(x)
+    _check_tables(grid, tables)
+    P = x.shape[0]
+    feat = torch.empty((P, 2 * grid.n_levels), dtype=torch.float32, device=x.device)
+    keep = torch.empty((P,), dtype=torch.bool, device=x.device)
+    with _guard(x):
+        call("pn_hash_encode_fwd", ctypes.byref(grid), _ptr_array(tables), dptr(qparams, allow_none=True),
+             dptr(x), P, dptr(feat), dptr(keep, torch.bool), stream())
+    return feat, keep
+
+
+def hash_encode_bwd(grid, dtables, x, dfeat):
+    """Accumulate the dense table gradients into dtables (list of [T,2], caller-zeroed)."""
+    x, dfeat = fcontig(x), fcontig(dfeat)
+    _check_tables(grid, dtables)
+    with _guard(x):
+        call("pn_hash_encode_bwd", ctypes.byref(grid), _ptr_array(dtables), dptr(x), dptr(dfeat), x.shape[0],
+             stream())
+
+
+def hash_indices(grid, x):
+    x = fcontig(x)
+    idx = torch.empty((x.shape[0], grid.n_levels, 8), dtype=torch.int32, device=x.device)
+    with _guard(x):
+        call("pn_hash_indices", ctypes.byref(grid), dptr(x), x.shape[0], dptr(idx, torch.int32), stream())
+    return idx
+
+
+def hash_coords(coords, log2_hashmap_size):
+    """utils.hash (utils.py:13-24) for integer coords[..., D<=3]."""
+    c = coords.to(torch.int64).contiguous()
+    out = torch.empty(c.shape[:-1], dtype=torch.int64, device=c.device)
+    n = out.numel()
+    with _guard(c):
+        call("pn_hash_coords", dptr(c, torch.int64), n, c.shape[-1], int(log2_hashmap_size), dptr(out, torch.int64),
+             stream())
+    return out
+
+
+def hash_gather_minmax(grid, tables, x):
+    x = fcontig(x)
+    _check_tables(grid, tables)
+    mm = torch.empty((grid.n_levels, 2), dtype=torch.float32, device=x.device)
+    mm[:, 0] = float("inf")
+    mm[:, 1] = float("-inf")
+    with _guard(x):
+        call("pn_hash_gather_minmax", ctypes.byref(grid), _ptr_array(tables), dptr(x), x.shape[0], dptr(mm), stream())
+    return mm
+
+
+class HashEncodeFn(torch.autograd.Function):
+    """feat, keep = HashEncodeFn.apply(x, grid, qparams, *tables).  Gradients flow to the tables only:
+    sample positions never require grad on this path (z_samples is detached, run_nerf.py:510)."""
+
+    @staticmethod
+    def forward(ctx, x, grid, qparams, *tables):
+        feat, keep = hash_encode_fwd(grid, [t.detach() for t in tables], x, qparams)
+        ctx.grid = grid
+        ctx.save_for_backward(x, *tables)
+        ctx.mark_non_differentiable(keep)
+        return feat, keep
+
+    @staticmethod
+    def backward(ctx, dfeat, _dkeep):
+        x, *tables = ctx.saved_tensors
+        grads = [None] * len(tables)
+        if dfeat is not None and any(ctx.needs_input_grad[3:]):
+            flat = torch.zeros((len(tables),) + tuple(tables[0].shape), dtype=torch.float32, device=x.device)
+            hash_encode_bwd(ctx.grid, list(flat.unbind(0)), x, dfeat)
+            grads = [flat[l] if ctx.needs_input_grad[3 + l] else None for l in range(len(tables))]
+        return (None, None, None) + tuple(grads)
+
+
+# ---------------------------------------------------------------------------------------------------
+# view directions
+# ---------------------------------------------------------------------------------------------------
+def sh_encode(dirs):
+    """hash_encoding.py:153-191, degree 4."""
+    d = fcontig(dirs.reshape(-1, 3))
+    out = torch.empty((d.shape[0], 16), dtype=torch.float32, device=d.device)
+    with _guard(d):
+        call("pn_sh_encode", dptr(d), d.shape[0], dptr(out), stream())
+    return out.reshape(*dirs.shape[:-1], 16)
+
+
+# ---------------------------------------------------------------------------------------------------
+# NeRFSmall
+# ---------------------------------------------------------------------------------------------------
+def _weights_struct(w):
+    s = MlpWeights()
+    for k in _MLP_KEYS:
+        t = w.get(k)
+        setattr(s, k, None if t is None else dptr(t))
+    return s
+
+
+def _rowptr(t, width):
+    """Pointer + row stride of a 2-D fp32 CUDA tensor whose rows are contiguous (a column slice of a wider
+    tensor is fine)."""
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == width
+            and (t.stride(1) == 1 or t.shape[1] == 1)):
+        raise _lib.PocketNerfError("expected a CUDA fp32 [n,%d] tensor with contiguous rows" % width)
+    stride = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), width)
+    return ctypes.c_void_p(t.data_ptr()), stride
+
+
+def _mlp_input(feat, sh, dirs, samples_per_ray, act_q, keep):
+    i = MlpInput()
+    i.feat, i.feat_stride = _rowptr(feat, 32)
+    i.sh, i.sh_stride = _rowptr(sh, 16) if sh is not None else (None, 0)
+    i.dirs = dptr(dirs) if dirs is not None else None
+    i.samples_per_ray = int(samples_per_ray)
+    i.act_q = dptr(act_q, allow_none=True)
+    i.keep = dptr(keep, torch.bool, allow_none=True)
+    i.n_points = feat.shape[0]
+    return i
+
+
+def mlp_fwd(w, feat, sh=None, dirs=None, samples_per_ray=1, act_q=None, keep=None):
+    """w: dict of contiguous fp32 CUDA weights (keys s0,s1,c0,c1,c2[,n0w,n0b,n2w,n2b]).  Returns
+    out[P, 4|7].   Reference: run_nerf_helpers.py:265-306 (+ run_nerf.py:59-66 when dirs/keep given)."""
+    C = 7 if w.get("n0w") is not None else 4
+    out = torch.empty((feat.shape[0], C), dtype=torch.float32, device=feat.device)
+    with _guard(feat):
+        ws, inp = _weights_struct(w), _mlp_input(feat, sh, dirs, samples_per_ray, act_q, keep)
+        call("pn_mlp_fwd", ctypes.byref(ws), ctypes.byref(inp), dptr(out), stream())
+    return out
+
+
+def mlp_bwd(w, feat, dout, sh=None, dirs=None, samples_per_ray=1, act_q=None, keep=None, want_dsh=False):
+    """Returns dfeat[P,32], dsh[P,16] or None, dict of weight gradients."""
+    dout = fcontig(dout)
+    P = feat.shape[0]
+    dfeat = torch.empty((P, 32), dtype=torch.float32, device=feat.device)
+    dsh = torch.empty((P, 16), dtype=torch.float32, device=feat.device) if (want_dsh and sh is not None) else None
+    dw = {k: torch.zeros_like(w[k]) for k in _MLP_KEYS if w.get(k) is not None}
+    with _guard(feat):
+        ws, inp = _weights_struct(w), _mlp_input(feat, sh, dirs, samples_per_ray, act_q, keep)
+        gs = _weights_struct(dw)
+        call("pn_mlp_bwd", ctypes.byref(ws), ctypes.byref(inp), dptr(dout), dptr(dfeat), 32,
+             dptr(dsh, allow_none=True), 16, ctypes.byref(gs), stream())
+    return dfeat, dsh, dw
+
+
+class MlpFn(torch.autograd.Function):
+    """out = MlpFn.apply(x48, act_q, n_weights, *weights) — NeRFSmall.forward on [B,48] inputs."""
+
+    @staticmethod
+    def forward(ctx, x, act_q, keys, *weights):
+        x = fcontig(x)
+        w = {k: fcontig(t.detach()) for k, t in zip(keys, weights)}
+        feat, sh = x[:, :32], x[:, 32:48]
+        out = mlp_fwd(w, feat, sh=sh, act_q=act_q)
+        ctx.keys, ctx.act_q = keys, act_q
+        ctx.save_for_backward(x, *weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, *weights = ctx.saved_tensors
+        w = {k: fcontig(t.detach()) for k, t in zip(ctx.keys, weights)}
+        dfeat, dsh, dw = mlp_bwd(w, x[:, :32], dout, sh=x[:, 32:48], act_q=ctx.act_q, want_dsh=True)
+        dx = torch.cat([dfeat, dsh], -1) if ctx.needs_input_grad[0] else None
+        return (dx, None, None) + tuple(dw[k] for k in ctx.keys)
+
+
+class FieldFn(torch.autograd.Function):
+    """raw[P, 4|7] = FieldFn.apply(pts[P,3], viewdirs[N,3], S, grid, qparams, act_q, keys, n_tables,
+    *tables, *weights): hash encode -> SH -> NeRFSmall -> keep-mask, i.e. run_network
+    (run_nerf.py:53-68) as one autograd node.  The feature tensor is kept for the backward; the table
+    gradients come out as views of one flat [L,T,2] buffer so that data-parallel training can
+    all-reduce them in one call."""
+
+    @staticmethod
+    def forward(ctx, pts, viewdirs, S, grid, qparams, act_q, keys, n_tables, *params):
+        tables, weights = params[:n_tables], params[n_tables:]
+        pts = fcontig(pts)
+        dirs = fcontig(viewdirs)
+        w = {k: fcontig(t.detach()) for k, t in zip(keys, weights)}
+        feat, keep = hash_encode_fwd(grid, [t.detach() for t in tables], pts, qparams)
+        out = mlp_fwd(w, feat, dirs=dirs, samples_per_ray=S, act_q=act_q, keep=keep)
+        ctx.grid, ctx.S, ctx.act_q, ctx.keys, ctx.n_tables = grid, S, act_q, keys, n_tables
+        ctx.save_for_backward(pts, dirs, feat, keep, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        pts, dirs, feat, keep, *params = ctx.saved_tensors
+        tables, weights = params[:ctx.n_tables], params[ctx.n_tables:]
+        w = {k: fcontig(t.detach()) for k, t in zip(ctx.keys, weights)}
+        dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep)
+        tgrads = [None] * ctx.n_tables
+        if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):
+            flat = torch.zeros((ctx.n_tables,) + tuple(tables[0].shape), dtype=torch.float32, device=pts.device)
+            hash_encode_bwd(ctx.grid, list(flat.unbind(0)), pts, dfeat)
+            tgrads = list(flat.unbind(0))
+        return (None,) * 8 + tuple(tgrads) + tuple(dw[k] for k in ctx.keys)
+
+
+# ---------------------------------------------------------------------------------------------------
+# compositing
+# ---------------------------------------------------------------------------------------------------
+class CompositeFn(torch.autograd.Function):
+    """(rgb, disp, acc, weights, depth, sparsity, normal|None) = CompositeFn.apply(raw, z, rays_d,
+    noise|None, white_bkgd) — raw2outputs (run_nerf.py:347-411)."""
+
+    @staticmethod
+    def forward(ctx, raw, z, rays_d, noise, white):
+        raw, z, rays_d = fcontig(raw), fcontig(z), fcontig(rays_d)
+        noise = fcontig(noise) if noise is not None else None
+        N, S, C = raw.shape
+        dev = raw.device
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        rgb, disp, acc, wts, depth, sp = f(N, 3), f(N), f(N), f(N, S), f(N), f(N)
+        normal = f(N, 3) if C == 7 else None
+        with _guard(raw):
+            call("pn_composite_fwd", dptr(raw), C, dptr(z), dptr(rays_d), dptr(noise, allow_none=True), N, S,
+                 int(bool(white)), dptr(rgb), dptr(disp), dptr(acc), dptr(wts), dptr(depth), dptr(sp),
+                 dptr(normal, allow_none=True), stream())
+        ctx.white = bool(white)
+        ctx.save_for_backward(raw, z, rays_d, noise)
+        ctx.set_materialize_grads(False)
+        if normal is None:
+            return rgb, disp, acc, wts, depth, sp
+        return rgb, disp, acc, wts, depth, sp, normal
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_disp, d_acc, d_wts, d_depth, d_sp, d_normal=None):
+        raw, z, rays_d, noise = ctx.saved_tensors
+        N, S, C = raw.shape
+        draw = torch.empty_like(raw)
+        c = lambda t: fcontig(t) if t is not None else None
+        d_rgb, d_disp, d_acc, d_wts, d_depth, d_sp, d_normal = map(c, (d_rgb, d_disp, d_acc, d_wts, d_depth, d_sp, d_normal))
+        with _guard(raw):
+            call("pn_composite_bwd", dptr(raw), C, dptr(z), dptr(rays_d), dptr(noise, allow_none=True), N, S,
+                 int(ctx.white), *[dptr(t, allow_none=True) for t in (d_rgb, d_disp, d_acc, d_wts, d_depth, d_sp, d_normal)],
+                 dptr(draw), stream())
+        return draw, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# sampling, sorting, rays
+# ---------------------------------------------------------------------------------------------------
+def _u_arg(u, N, M):
+    u = fcontig(u)
+    if u.dim() == 1:
+        return u, 0
+    if tuple(u.shape) != (N, M):
+        raise _lib.PocketNerfError("u shape %s != (%d, %d)" % (tuple(u.shape), N, M))
+    return u, M
+
+
+def sample_pdf(bins, weights, u, return_inds=False, return_cdf=False):
+    """bins[N,nb], weights[N,nb-1] (any row stride), u[N,M] or [M] (broadcast).  Not differentiable
+    (the reference detaches the result, run_nerf.py:510)."""
+    bins = fcontig(bins.detach())
+    weights = weights.detach()
+    if weights.dtype != torch.float32 or weights.stride(-1) != 1:
+        weights = fcontig(weights)
+    N, nb = bins.shape
+    M = u.shape[-1]
+    u, us = _u_arg(u.detach(), N, M)
+    samples = torch.empty((N, M), dtype=torch.float32, device=bins.device)
+    inds = torch.empty((N, M), dtype=torch.int32, device=bins.device) if return_inds else None
+    cdf = torch.empty((N, nb), dtype=torch.float32, device=bins.device) if return_cdf else None
+    with _guard(bins):
+        call("pn_sample_pdf", dptr(bins), ctypes.c_void_p(weights.data_ptr()), weights.stride(0), dptr(u), us, N, nb, M,
+             dptr(samples), dptr(inds, torch.int32, allow_none=True), dptr(cdf, allow_none=True), stream())
+    out = (samples,)
+    if return_inds:
+        out += (inds,)
+    if return_cdf:
+        out += (cdf,)
+    return out if len(out) > 1 else samples
+
+
+def sample_from_cdf(cdf, bins, u):
+    cdf, bins = fcontig(cdf), fcontig(bins)
+    N, nb = bins.shape
+    M = u.shape[-1]
+    u, us = _u_arg(u, N, M)
+    samples = torch.empty((N, M), dtype=torch.float32, device=bins.device)
+    inds = torch.empty((N, M), dtype=torch.int32, device=bins.device)
+    with _guard(bins):
+        call("pn_sample_from_cdf", dptr(cdf), dptr(bins), dptr(u), us, N, nb, M, dptr(samples),
+             dptr(inds, torch.int32), stream())
+    return samples, inds
+
+
+def sort_merge(a, b):
+    """torch.sort(torch.cat([a, b], -1), -1)[0] for 2-D inputs (run_nerf.py:512)."""
+    a, b = fcontig(a.detach()), fcontig(b.detach())
+    N = a.shape[0]
+    out = torch.empty((N, a.shape[1] + b.shape[1]), dtype=torch.float32, device=a.device)
+    with _guard(a):
+        call("pn_sort_merge", dptr(a), a.shape[1], dptr(b), b.shape[1], N, dptr(out), stream())
+    return out
+
+
+def gen_rays(H, W, K, c2w, device):
+    """get_rays (run_nerf_helpers.py:311-320).  K: 3x3 array-like (host), c2w: [3,4] (host or device)."""
+    Kf = (ctypes.c_float * 9)(*[float(K[i][j]) for i in range(3) for j in range(3)])
+    c = c2w.detach().cpu().tolist() if torch.is_tensor(c2w) else [list(r) for r in c2w]
+    Cf = (ctypes.c_float * 12)(*[float(c[i][j]) for i in range(3) for j in range(4)])
+    rays_o = torch.empty((H, W, 3), dtype=torch.float32, device=device)
+    rays_d = torch.empty((H, W, 3), dtype=torch.float32, device=device)
+    with _guard(rays_o):
+        call("pn_gen_rays", int(H), int(W), Kf, Cf, dptr(rays_o), dptr(rays_d), stream())
+    return rays_o, rays_d
+
+
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """run_nerf_helpers.py:333-350."""
+    shape = rays_o.shape
+    o, d = fcontig(rays_o.reshape(-1, 3)), fcontig(rays_d.reshape(-1, 3))
+    oo, od = torch.empty_like(o), torch.empty_like(d)
+    with _guard(o):
+        call("pn_ndc_rays", int(H), int(W), float(focal), float(near), dptr(o), dptr(d), o.shape[0], dptr(oo), dptr(od),
+             stream())
+    return oo.reshape(shape), od.reshape(shape)
+
+
+def make_points(rays_o, rays_d, z):
+    """pts[N,S,3] = o + d*z (run_nerf.py:490,513); rays_o/rays_d may be strided row views."""
+    z = fcontig(z)
+    N, S = z.shape
+
+    def rows(t):
+        if t.dtype != torch.float32 or t.stride(-1) != 1:
+            t = fcontig(t)
+        return t
+
+    o, d = rows(rays_o), rows(rays_d)
+    pts = torch.empty((N, S, 3), dtype=torch.float32, device=z.device)
+    with _guard(z):
+        call("pn_make_points", ctypes.c_void_p(o.data_ptr()), o.stride(0), ctypes.c_void_p(d.data_ptr()), d.stride(0),
+             dptr(z), N, S, dptr(pts), stream())
+    return pts
+
+
+def coarse_z(near, far, t_vals, t_rand=None, lindisp=False):
+    """run_nerf.py:466-488.  near/far: [N] or [N,1] views (row stride allowed); t_vals[S]."""
+    N = near.shape[0]
+    S = t_vals.shape[0]
+    if near.stride(0) != far.stride(0) or near.dtype != torch.float32 or far.dtype != torch.float32:
+        near, far = fcontig(near.reshape(N)), fcontig(far.reshape(N))
+    t_vals = fcontig(t_vals)
+    t_rand = fcontig(t_rand) if t_rand is not None else None
+    z = torch.empty((N, S), dtype=torch.float32, device=t_vals.device)
+    with _guard(z):
+        call("pn_coarse_z", ctypes.c_void_p(near.data_ptr()), ctypes.c_void_p(far.data_ptr()), near.stride(0),
+             dptr(t_vals), dptr(t_rand, allow_none=True), N, S, int(bool(lindisp)), dptr(z), stream())
+    return z

@@ -1,0 +1,183 @@
+"""Drop-in for the renderer functions that live inside the reference's run_nerf.py: batchify,
+run_network, batchify_rays, render, raw2outputs, render_rays (run_nerf.py:43-151, 347-549).
+
+Same signatures, same return structure, same use of torch's global RNG; the arithmetic runs in the
+sm_100a kernels (ops.py).  ``patch(run_nerf_module)`` installs them into an imported reference driver.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .hash_encoding import HashEmbedder, SHEncoder
+from .run_nerf_helpers import NeRFSmall, get_rays, ndc_rays, sample_pdf
+
+
+def batchify(fn, chunk):
+    """run_nerf.py:43-50."""
+    if chunk is None:
+        return fn
+
+    def ret(inputs):
+        return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+    return ret
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """run_nerf.py:53-68.  With our HashEmbedder + SHEncoder + NeRFSmall the whole function is one
+    autograd node (hash encode -> SH -> MLP -> keep mask); any other combination of callables goes
+    through the generic composition below, still on the GPU."""
+    if (isinstance(embed_fn, HashEmbedder) and isinstance(fn, NeRFSmall) and viewdirs is not None
+            and isinstance(embeddirs_fn, SHEncoder) and inputs.dim() == 3):
+        N, S = inputs.shape[0], inputs.shape[1]
+        if embed_fn.training:
+            embed_fn.current_step += 1                                   # hash_encoding.py:83-84
+        if not embed_fn._is_flat():
+            embed_fn._reflatten()
+        pts = inputs.reshape(-1, 3)
+        qrows = embed_fn._quant_rows(pts.detach())
+        keys, weights = fn.kernel_weights()
+        act_q = None
+        if fn.use_quantization and fn.sigma_act_quantizers is not None:
+            feat0 = None
+            if fn.training and not fn.sigma_act_quantizers[0].calibrated:
+                # the reference calibrates on the first netchunk of the first training call (run_nerf.py:65)
+                feat0, _ = ops.hash_encode_fwd(embed_fn.grid(), [t.detach() for t in embed_fn.tables()],
+                                               pts.detach()[:netchunk], qrows)
+            act_q = fn.act_qrow(feat0, weights[0])
+        tables = embed_fn.tables()
+        out = ops.FieldFn.apply(pts, viewdirs, S, embed_fn.grid(), qrows, act_q, keys, len(tables), *tables, *weights)
+        return out.reshape(N, S, out.shape[-1])
+
+    inputs_flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded, keep_mask = embed_fn(inputs_flat)
+    if viewdirs is not None:
+        input_dirs = viewdirs[:, None].expand(inputs.shape)
+        embedded_dirs = embeddirs_fn(torch.reshape(input_dirs, [-1, input_dirs.shape[-1]]))
+        embedded = torch.cat([embedded, embedded_dirs], -1)
+    outputs_flat = batchify(fn, netchunk)(embedded)
+    outputs_flat = outputs_flat.clone()
+    outputs_flat[~keep_mask, -1] = 0
+    return torch.reshape(outputs_flat, list(inputs.shape[:-1]) + [outputs_flat.shape[-1]])
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False, predict_normals=False):
+    """run_nerf.py:347-411 -> (rgb_map, disp_map, acc_map, weights, depth_map, sparsity_loss[, normal_map])."""
+    noise = None
+    if raw_noise_std > 0.:
+        noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std
+        if pytest:
+            np.random.seed(0)
+            noise = torch.tensor(np.random.rand(*list(raw[..., 3].shape)) * raw_noise_std, dtype=torch.float32,
+                                 device=raw.device)
+    out = ops.CompositeFn.apply(raw, z_vals, rays_d, noise, bool(white_bkgd))
+    if predict_normals:
+        if raw.shape[-1] != 7:
+            raise ValueError("predict_normals needs a 7-channel raw tensor (network with a normal head)")
+        return out
+    return out[:6]
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, embed_fn=None, retraw=False, lindisp=False,
+                perturb=0., N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False,
+                pytest=False, predict_normals=False):
+    """run_nerf.py:414-549."""
+    N_rays = ray_batch.shape[0]
+    dev = ray_batch.device
+    rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+    viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None
+    near, far = ray_batch[:, 6], ray_batch[:, 7]
+
+    t_vals = torch.linspace(0., 1., steps=N_samples, device=dev)
+    t_rand = None
+    if perturb > 0.:
+        t_rand = torch.rand([N_rays, N_samples], device=dev)
+        if pytest:
+            np.random.seed(0)
+            t_rand = torch.tensor(np.random.rand(N_rays, N_samples), dtype=torch.float32, device=dev)
+    z_vals = ops.coarse_z(near, far, t_vals, t_rand, lindisp)
+    pts = ops.make_points(rays_o, rays_d, z_vals)
+
+    raw = network_query_fn(pts, viewdirs, network_fn)
+    outs = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd, pytest=pytest, predict_normals=predict_normals)
+    rgb_map, disp_map, acc_map, weights, depth_map, sparsity_loss = outs[:6]
+    normal_map = outs[6] if predict_normals else None
+
+    if N_importance > 0:
+        rgb_map_0, depth_map_0, acc_map_0, sparsity_loss_0, normal_map_0 = rgb_map, depth_map, acc_map, sparsity_loss, normal_map
+        z_vals_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        z_samples = sample_pdf(z_vals_mid, weights[..., 1:-1], N_importance, det=(perturb == 0.), pytest=pytest)
+        z_samples = z_samples.detach()
+        z_vals = ops.sort_merge(z_vals, z_samples)
+        pts = ops.make_points(rays_o, rays_d, z_vals)
+        run_fn = network_fn if network_fine is None else network_fine
+        raw = network_query_fn(pts, viewdirs, run_fn)
+        outs = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd, pytest=pytest, predict_normals=predict_normals)
+        rgb_map, disp_map, acc_map, weights, depth_map, sparsity_loss = outs[:6]
+        normal_map = outs[6] if predict_normals else None
+
+    ret = {"rgb_map": rgb_map, "depth_map": depth_map, "acc_map": acc_map, "sparsity_loss": sparsity_loss}
+    ret["pts"] = pts
+    ret["rays_d"] = rays_d
+    if predict_normals:
+        ret["normal_map"] = normal_map
+    if retraw:
+        ret["raw"] = raw
+    if N_importance > 0:
+        ret["rgb0"] = rgb_map_0
+        ret["depth0"] = depth_map_0
+        ret["acc0"] = acc_map_0
+        ret["sparsity_loss0"] = sparsity_loss_0
+        ret["z_std"] = torch.std(z_samples, dim=-1, unbiased=False)
+        if predict_normals:
+            ret["normal0"] = normal_map_0
+    return ret
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """run_nerf.py:71-83."""
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k in ret:
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
+
+
+def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, **kwargs):
+    """run_nerf.py:86-151 -> [rgb_map, depth_map, acc_map, extras]."""
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, K, c2w)
+    else:
+        rays_o, rays_d = rays
+    viewdirs = None
+    if use_viewdirs:
+        viewdirs = rays_d
+        if c2w_staticcam is not None:
+            rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
+        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+    sh = rays_d.shape
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    parts = [rays_o, rays_d, near, far]
+    if use_viewdirs:
+        parts.append(viewdirs)
+    rays = torch.cat(parts, -1)
+
+    all_ret = batchify_rays(rays, chunk, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    k_extract = ["rgb_map", "depth_map", "acc_map"]
+    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+
+def patch(run_nerf_module):
+    """Install the renderer into an imported reference driver (`import run_nerf; patch(run_nerf)`):
+    the driver's train()/render_path() then run on the kernels.  See INTEGRATION.md."""
+    for name in ("batchify", "run_network", "batchify_rays", "render", "raw2outputs", "render_rays"):
+        setattr(run_nerf_module, name, globals()[name])
+    return run_nerf_module

@@ -1,0 +1,53 @@
+"""One optimisation step of the reference's training loop (run_nerf.py:1007-1162) around the kernels:
+render the ray batch, image + sparsity + TV losses, backward, (data-parallel gradient all-reduce),
+RAdam.  The structural-prior losses are callers of this path (they consume depth_map / normal_map) and
+stay in the reference's own torch code."""
+import torch
+
+from . import parallel
+from .loss import total_variation_loss
+from .render import render
+from .run_nerf_helpers import img2mse, mse2psnr
+
+
+class Trainer:
+    def __init__(self, args, render_kwargs_train, optimizer, H, W, K, near, far, group=None):
+        self.args, self.kw, self.opt = args, dict(render_kwargs_train), optimizer
+        self.H, self.W, self.K, self.near, self.far = H, W, K, near, far
+        self.group = group
+        self.world = parallel.world_size(group)
+        self.tv_weight = args.tv_loss_weight
+        self.step_idx = 0
+        self.embed_fn = self.kw["embed_fn"]
+        self.nets = [self.kw["network_fn"]] + ([self.kw["network_fine"]] if self.kw.get("network_fine") is not None else [])
+
+    def losses(self, rgb, extras, target_s):
+        """run_nerf.py:1010-1037.  With a process group the terms are scaled so that the SUM of the ranks'
+        gradients is the gradient of the single-process loss over the concatenated batch."""
+        w = float(self.world)
+        img_loss = img2mse(rgb, target_s)
+        loss = img_loss / w
+        if "rgb0" in extras:
+            loss = loss + img2mse(extras["rgb0"], target_s) / w
+        sparsity = self.args.sparse_loss_weight * (extras["sparsity_loss"].sum() + extras["sparsity_loss0"].sum())
+        loss = loss + sparsity
+        e = self.embed_fn
+        tv = sum(total_variation_loss(e.embeddings[i], e.base_resolution, e.finest_resolution, i, e.log2_hashmap_size,
+                                      n_levels=e.n_levels) for i in range(e.n_levels))
+        loss = loss + self.tv_weight * tv / w
+        return loss, img_loss
+
+    def step(self, batch_rays, target_s, chunk=None):
+        """batch_rays [2,N,3], target_s [N,3] (this rank's shard).  Returns (loss, psnr) as 0-d device tensors."""
+        rgb, depth, acc, extras = render(self.H, self.W, self.K, chunk=chunk or batch_rays.shape[1], rays=batch_rays,
+                                         retraw=True, near=self.near, far=self.far, **self.kw)
+        self.opt.zero_grad()
+        loss, img_loss = self.losses(rgb, extras, target_s)
+        loss.backward()
+        if self.world > 1:
+            parallel.allreduce_gradients(self.embed_fn, self.nets, self.group)
+        self.opt.step()
+        self.step_idx += 1
+        if self.step_idx > 1000:                                   # run_nerf.py:1036-1037
+            self.tv_weight = 0.0
+        return loss.detach(), mse2psnr(img_loss.detach())

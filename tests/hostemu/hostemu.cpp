@@ -1,0 +1,113 @@
+// TEST INFRASTRUCTURE — host build of the kernels' per-element arithmetic.
+//
+// The bit-exact parts of the CUDA path (hash cell / index / trilinear interpolation / fake-quant, SH,
+// cdf inversion, ray generation, coarse depths, o + d*z) are written once as host/device functions in
+// indoor-nerf_b200/csrc/*_core.cuh.  This file compiles those same functions for the host (g++,
+// -ffp-contract=off) behind a tiny C interface so that the CPU test-suite can check them against the
+// golden vectors without a GPU.  It is loaded by tests/test_hostemu.py only; the product library
+// (libpocketnerf.so) contains none of it and has no CPU path.
+#include "../../indoor-nerf_b200/csrc/hash_core.cuh"
+#include "../../indoor-nerf_b200/csrc/ray_core.cuh"
+#include "../../indoor-nerf_b200/csrc/sample_core.cuh"
+
+using namespace pn;
+
+extern "C" {
+
+void emu_hash_encode(const pn_hash_grid *grid, const float *const *tables, const float *qparams, const float *x,
+                     int64_t P, float *feat, uint8_t *keep, int32_t *idx) {
+  const HashGridDev G = make_grid_dev(*grid);
+  const int L = G.n_levels;
+  for (int64_t p = 0; p < P; ++p) {
+    const float xv[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+    for (int l = 0; l < L; ++l) {
+      Cell c;
+      point_cell(G, l, xv, c);
+      float e0[8], e1[8];
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t h = corner_index(G, c, k);
+        if (idx) idx[(p * L + l) * 8 + k] = (int32_t)h;
+        e0[k] = tables[l][2 * h];
+        e1[k] = tables[l][2 * h + 1];
+        if (qparams && qparams[l * PN_QROW + 5] != 0.f) {
+          const float *q = qparams + l * PN_QROW;
+          e0[k] = fake_quant(e0[k], q[0], q[1], q[2], q[3], q[4], q[6] != 0.f);
+          e1[k] = fake_quant(e1[k], q[0], q[1], q[2], q[3], q[4], q[6] != 0.f);
+        }
+      }
+      feat[p * 2 * L + 2 * l] = trilerp(e0, c.w);
+      feat[p * 2 * L + 2 * l + 1] = trilerp(e1, c.w);
+    }
+    if (keep) keep[p] = point_keep(G, xv) ? 1 : 0;
+  }
+}
+
+void emu_hash_bwd(const pn_hash_grid *grid, float *const *dtables, const float *x, const float *dfeat, int64_t P) {
+  const HashGridDev G = make_grid_dev(*grid);
+  const int L = G.n_levels;
+  for (int64_t p = 0; p < P; ++p) {
+    const float xv[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+    for (int l = 0; l < L; ++l) {
+      Cell c;
+      point_cell(G, l, xv, c);
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t h = corner_index(G, c, k);
+        dtables[l][2 * h] += corner_weight_times(dfeat[p * 2 * L + 2 * l], c.w, k);
+        dtables[l][2 * h + 1] += corner_weight_times(dfeat[p * 2 * L + 2 * l + 1], c.w, k);
+      }
+    }
+  }
+}
+
+void emu_sh4(const float *dirs, int64_t n, float *out) {
+  for (int64_t i = 0; i < n; ++i) sh4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], out + 16 * i);
+}
+
+void emu_sample_from_cdf(const float *cdf, const float *bins, const float *u, int64_t u_stride, int64_t N, int nb,
+                         int M, float *samples, int32_t *inds) {
+  for (int64_t r = 0; r < N; ++r)
+    for (int j = 0; j < M; ++j) {
+      int ind;
+      samples[r * M + j] = invert_cdf(cdf + r * nb, bins + r * nb, nb, u[r * u_stride + j], &ind);
+      if (inds) inds[r * M + j] = ind;
+    }
+}
+
+void emu_gen_rays(int H, int W, const float *K, const float *c2w, float *rays_o, float *rays_d) {
+  Cam cam;
+  cam.fx = K[0]; cam.cx = K[2]; cam.fy = K[4]; cam.cy = K[5];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) cam.R[r][c] = c2w[4 * r + c];
+    cam.t[r] = c2w[4 * r + 3];
+  }
+  for (int j = 0; j < H; ++j)
+    for (int i = 0; i < W; ++i) {
+      float d[3];
+      ray_dir(cam, i, j, d);
+      for (int c = 0; c < 3; ++c) {
+        rays_d[3 * ((int64_t)j * W + i) + c] = d[c];
+        rays_o[3 * ((int64_t)j * W + i) + c] = cam.t[c];
+      }
+    }
+}
+
+void emu_make_points(const float *o, const float *d, const float *z, int64_t N, int S, float *pts) {
+  for (int64_t r = 0; r < N; ++r)
+    for (int s = 0; s < S; ++s)
+      for (int c = 0; c < 3; ++c) pts[3 * (r * S + s) + c] = point_at(o[3 * r + c], d[3 * r + c], z[r * S + s]);
+}
+
+void emu_coarse_z(const float *near, const float *far, const float *t_vals, const float *t_rand, int64_t N, int S,
+                  int lindisp, float *z) {
+  for (int64_t r = 0; r < N; ++r)
+    for (int s = 0; s < S; ++s)
+      z[r * S + s] = coarse_z_at(near[r], far[r], t_vals, s, S, lindisp != 0, t_rand ? &t_rand[r * S + s] : nullptr);
+}
+
+void emu_ndc_rays(int H, int W, double focal, double near, const float *o, const float *d, int64_t n, float *oo,
+                  float *od) {
+  const float cw = (float)(-1.0 / (W / (2.0 * focal))), ch = (float)(-1.0 / (H / (2.0 * focal)));
+  for (int64_t p = 0; p < n; ++p) ndc_ray(cw, ch, (float)near, (float)(2.0 * near), o + 3 * p, d + 3 * p, oo + 3 * p, od + 3 * p);
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""CPU-side checks of the host layer: the C-ABI library loads and exports what include/pocketnerf.h
+declares, the drop-in modules keep the reference's names / state_dict keys / parameter order, the torch-side
+pieces (RAdam, TV loss) match the golden vectors, and nothing silently runs on the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import indoor_nerf_b200 as pn
+from indoor_nerf_b200 import _lib, loss as ploss, model as pmodel, radam as pradam, utils as putils
+from oracle.fixtures import synthetic_tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+T = torch.from_numpy
+
+
+def test_library_exports_header_symbols():
+    header = open(os.path.join(ROOT, "include", "pocketnerf.h")).read()
+    declared = set(re.findall(r"\b(pn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"pn_stream_t"}
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libpocketnerf.so does not export %s" % name
+    assert set(_lib.exported_symbols()) <= declared | {"pn_abi_version", "pn_last_error", "pn_launch_count"}
+    assert declared == set(_lib.exported_symbols()), "binding and header disagree: %s" % (
+        declared ^ set(_lib.exported_symbols()))
+    assert _lib.lib().pn_abi_version() == int(re.search(r"#define PN_ABI_VERSION (\d+)", header).group(1))
+
+
+def test_no_cpu_path():
+    emb = pn.HashEmbedder((torch.tensor([-1.0] * 3), torch.tensor([1.0] * 3)), log2_hashmap_size=8)
+    with pytest.raises(_lib.PocketNerfError):
+        emb(torch.zeros(4, 3))
+    net = pn.NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, input_ch=32, input_ch_views=16)
+    with pytest.raises(_lib.PocketNerfError):
+        net(torch.zeros(4, 48))
+    with pytest.raises(_lib.PocketNerfError):
+        pn.raw2outputs(torch.zeros(2, 8, 4), torch.zeros(2, 8), torch.zeros(2, 3))
+
+
+def test_bad_arguments_are_reported():
+    lib = _lib.lib()
+    g = _lib.HashGrid()
+    g.n_levels, g.log2_hashmap_size = 99, 19
+    rc = lib.pn_hash_encode_fwd(ctypes.byref(g), None, None, None, 0, None, None, None)
+    assert rc == -3 and b"n_levels" in lib.pn_last_error()
+    rc = lib.pn_sort_merge(None, 1, None, 1, 1, None, None)
+    assert rc == -1 and b"NULL" in lib.pn_last_error()
+
+
+def test_hash_embedder_layout_and_keys():
+    box = (torch.tensor([-1.5] * 3), torch.tensor([1.5] * 3))
+    emb = pn.HashEmbedder(box, log2_hashmap_size=10, use_quantization=True)
+    keys = list(emb.state_dict().keys())
+    assert keys[:16] == ["embeddings.%d.weight" % l for l in range(16)]
+    assert keys[16:21] == ["quantizers.0.soft_bits", "quantizers.0.range_scale", "quantizers.0.v_max",
+                           "quantizers.0.running_min", "quantizers.0.running_max"]
+    params = list(emb.parameters())
+    assert len(params) == 16 + 48 and all(p.shape == (1024, 2) for p in params[:16])
+    assert emb._is_flat() and emb.out_dim == 32 and emb.warmup_steps == 500 and emb.current_step == 0
+    assert float(emb.embeddings[3].weight.abs().max()) <= 1e-4
+    # state_dict round trip keeps the single-buffer layout; double() + float() (an _apply) re-flattens
+    sd = {k: v.clone() for k, v in emb.state_dict().items()}
+    emb2 = pn.HashEmbedder(box, log2_hashmap_size=10, use_quantization=True)
+    emb2.load_state_dict(sd)
+    assert emb2._is_flat() and torch.equal(emb2.table_storage, emb.table_storage)
+    emb2.double().float()
+    assert emb2._is_flat() and torch.equal(emb2.table_storage, emb.table_storage)
+    # the TV loss indexes a level with an int64 tensor of any shape
+    idx = torch.randint(0, 1024, (3, 4, 5))
+    assert emb.embeddings[2](idx).shape == (3, 4, 5, 2)
+    # resolutions (float32 knife edges)
+    assert [float(r) for r in emb.level_resolutions()] == [16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256,
+                                                           322, 406, 512]
+
+
+def test_nerf_small_keys_match_reference_names():
+    net = pn.NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, input_ch=32,
+                       input_ch_views=16, use_quantization=True, predict_normals=True)
+    keys = set(net.state_dict().keys())
+    assert {"sigma_net.0.weight", "sigma_net.1.weight", "color_net.0.weight", "color_net.1.weight",
+            "color_net.2.weight", "normal_net.0.weight", "normal_net.0.bias", "normal_net.2.weight",
+            "normal_net.2.bias", "sigma_act_quantizers.0.soft_bits", "sigma_weight_quantizer.soft_bits"} <= keys
+    assert net.sigma_net[0].weight.shape == (64, 32) and net.color_net[0].weight.shape == (64, 31)
+    assert sum(p.numel() for n, p in net.named_parameters() if "quantizer" not in n and "normal" not in n) == 9344
+
+
+@pytest.mark.live_reference
+def test_state_dict_keys_equal_live_reference():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference not present")
+    ref = ref_shim.load()
+    box = (torch.tensor([-1.5] * 3), torch.tensor([1.5] * 3))
+    for q in (False, True):
+        a = ref.hash_encoding.HashEmbedder(box, log2_hashmap_size=8, use_quantization=q)
+        b = pn.HashEmbedder(box, log2_hashmap_size=8, use_quantization=q)
+        assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+        assert [tuple(p.shape) for p in a.parameters()] == [tuple(p.shape) for p in b.parameters()]
+        for normals in (False, True):
+            ra = ref_shim.make_nerf_small(ref, predict_normals=normals, use_quantization=q)
+            rb = pn.NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, input_ch=32,
+                              input_ch_views=16, use_quantization=q, predict_normals=normals)
+            assert list(ra.state_dict().keys()) == list(rb.state_dict().keys())
+            assert [tuple(p.shape) for p in ra.parameters()] == [tuple(p.shape) for p in rb.parameters()]
+
+
+def test_quantizer_module_matches_oracle():
+    from oracle import hashnerf_oracle as O
+    x = torch.randn(64, 32) * 0.1
+    for sym in (True, False):
+        q = pn.LearnedBitwidthQuantizer(init_bits=6.3, symmetric=sym).train()
+        y = q(x)                                       # calibrates
+        rs, vmax, _, _ = O.lbq_calibrate(x, sym)
+        for training in (True, False):
+            q.train(training)
+            want = O.lbq_apply(x, *O.lbq_scalars(q.soft_bits.data, rs, vmax, sym, training), training)
+            assert torch.equal(q(x), want)
+        row = q.qrow(training=True)
+        assert row.shape == (8,) and float(row[5]) == 1.0
+
+
+def test_radam_golden(golden):
+    g = golden("radam")
+    p = [torch.nn.Parameter(T(g["init0"].copy())), torch.nn.Parameter(T(g["init1"].copy()))]
+    opt = pradam.RAdam([{"params": [p[0]], "weight_decay": 1e-6}, {"params": [p[1]], "eps": 1e-15}], lr=5e-4,
+                       betas=(0.9, 0.99))
+    for it in range(8):
+        for i in range(2):
+            p[i].grad = T(g["g%d_%d" % (it, i)].copy())
+        opt.step()
+        for i in range(2):
+            np.testing.assert_allclose(p[i].detach().numpy(), g["p%d_%d" % (it, i)], rtol=2e-6, atol=1e-9)
+    assert set(opt.state[p[0]].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_tv_loss_golden(golden):
+    g = golden("tv_loss")
+    table = torch.nn.Embedding(1 << 19, 2, _weight=T(synthetic_tables(1, 19, salt=int(g["salt"]))[0]))
+    for level in (0, 5, 15):
+        torch.manual_seed(100 + level)
+        v = ploss.total_variation_loss(table, torch.tensor(16), torch.tensor(512), level, 19, n_levels=16)
+        np.testing.assert_allclose(float(v), float(g["tv_%d" % level]), rtol=1e-6)
+
+
+def test_utils_hash_cpu_formula(golden):
+    g = golden("hash_primitives")
+    for k in (12, 19, 22):
+        assert (putils.hash(T(g["corners"]), k).numpy() == g["h%d" % k]).all()
+
+
+def test_create_nerf_structure():
+    a = pmodel.default_args(bounding_box=(torch.tensor([-2.0] * 3), torch.tensor([2.0] * 3)), log2_hashmap_size=8)
+    kw_train, kw_test, start, grad_vars, opt = pmodel.create_nerf(a, device="cpu")
+    assert set(kw_train) == {"network_query_fn", "perturb", "N_importance", "network_fine", "N_samples", "network_fn",
+                             "embed_fn", "use_viewdirs", "white_bkgd", "raw_noise_std", "predict_normals", "ndc", "lindisp"}
+    assert kw_test["perturb"] is False and kw_test["raw_noise_std"] == 0.
+    assert len(grad_vars) == 10 and start == 0
+    assert len(opt.param_groups) == 2 and opt.param_groups[0]["weight_decay"] == 1e-6 and opt.param_groups[1]["eps"] == 1e-15
+    assert len(opt.param_groups[1]["params"]) == 16
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    a = pmodel.default_args(bounding_box=(torch.tensor([-2.0] * 3), torch.tensor([2.0] * 3)), log2_hashmap_size=8)
+    kw, _, _, _, opt = pmodel.create_nerf(a, device="cpu")
+    d = tmp_path / "exp"
+    d.mkdir()
+    pmodel.save_checkpoint(str(d / "000123.tar"), 123, kw, opt)
+    a2 = pmodel.default_args(bounding_box=a.bounding_box, log2_hashmap_size=8, basedir=str(tmp_path), expname="exp",
+                             no_reload=False)
+    kw2, _, start, _, _ = pmodel.create_nerf(a2, device="cpu")
+    assert start == 123
+    assert torch.equal(kw2["embed_fn"].table_storage, kw["embed_fn"].table_storage)
+    assert torch.equal(kw2["network_fine"].color_net[1].weight, kw["network_fine"].color_net[1].weight)

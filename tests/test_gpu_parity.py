@@ -1,0 +1,455 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden vectors from the live reference
+(tests/golden) and the oracle run on the same seeded inputs.  Bars (BASELINE.json north_star):
+  hash indices, sample bins ............ bit-exact
+  embeddings, SH, rays, z, points ....... bit-exact (individually rounded fp32 ops reproduced)
+  MLP / compositing outputs, gradients .. 1e-5 relative (fp32 mode)
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hashnerf_oracle as O
+from oracle.fixtures import mlp_weights, synthetic_points, synthetic_tables
+
+pytestmark = pytest.mark.gpu
+
+T = torch.from_numpy
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pn():
+    import indoor_nerf_b200 as pkg
+    assert torch.cuda.is_available()
+    return pkg
+
+
+def cu(a):
+    return (T(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a).cuda()
+
+
+def close(a, b, rtol=RTOL, what=""):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    nan = np.isnan(b)
+    assert (np.isnan(a) == nan).all(), what + ": NaN pattern differs"
+    scale = np.abs(b[~nan]).max() if (~nan).any() else 1.0
+    err = np.abs(a[~nan] - b[~nan]).max() if (~nan).any() else 0.0
+    assert err <= rtol * max(scale, 1e-30), "%s: max err %.3e vs scale %.3e (rel %.2e > %.1e)" % (
+        what, err, scale, err / max(scale, 1e-30), rtol)
+
+
+def embedder_from(pn, box_min, box_max, log2T, finest, tables, **kw):
+    emb = pn.HashEmbedder((T(np.asarray(box_min, np.float32)), T(np.asarray(box_max, np.float32))),
+                          log2_hashmap_size=log2T, finest_resolution=finest, **kw)
+    with torch.no_grad():
+        for l in range(16):
+            emb.embeddings[l].weight.copy_(T(tables[l]))
+    return emb.cuda()
+
+
+def mlp_from(pn, w, **kw):
+    m = pn.NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                     input_ch=32, input_ch_views=16, predict_normals=("n0w" in w), **kw)
+    with torch.no_grad():
+        m.sigma_net[0].weight.copy_(w["s0"]); m.sigma_net[1].weight.copy_(w["s1"])
+        m.color_net[0].weight.copy_(w["c0"]); m.color_net[1].weight.copy_(w["c1"]); m.color_net[2].weight.copy_(w["c2"])
+        if "n0w" in w:
+            m.normal_net[0].weight.copy_(w["n0w"]); m.normal_net[0].bias.copy_(w["n0b"])
+            m.normal_net[2].weight.copy_(w["n2w"]); m.normal_net[2].bias.copy_(w["n2b"])
+    return m.cuda()
+
+
+def mlp_grads(m):
+    g = dict(s0=m.sigma_net[0].weight.grad, s1=m.sigma_net[1].weight.grad, c0=m.color_net[0].weight.grad,
+             c1=m.color_net[1].weight.grad, c2=m.color_net[2].weight.grad)
+    if m.predict_normals:
+        g.update(n0w=m.normal_net[0].weight.grad, n0b=m.normal_net[0].bias.grad, n2w=m.normal_net[2].weight.grad,
+                 n2b=m.normal_net[2].bias.grad)
+    return g
+
+
+# ------------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_hash_golden(pn, golden, tag):
+    g = golden("hash_embed_" + tag)
+    log2T = int(g["log2T"])
+    tables = synthetic_tables(16, log2T, salt=int(g["salt"]))
+    emb = embedder_from(pn, g["box_min"], g["box_max"], log2T, int(g["finest"]), tables).eval()
+    x = cu(g["x"])
+    idx = pn.ops.hash_indices(emb.grid(), x)
+    assert (idx.cpu().numpy() == g["idx"]).all(), "hash indices must be bit-exact"
+    feat, keep = emb(x)
+    assert (keep.cpu().numpy() == g["keep"]).all()
+    assert (feat.detach().cpu().numpy() == g["feat"]).all(), "embeddings must be bit-exact"
+    (feat * cu(g["dfeat"])).sum().backward()
+    grads = [e.weight.grad for e in emb.embeddings]
+    close(torch.stack([t.abs().sum() for t in grads]), g["grad_abs_sum"], what="grad |sum|")
+    for l in (0, 7, 15):
+        close(grads[l][cu(g["grad_rows_%d" % l])], g["grad_vals_%d" % l], what="grad rows level %d" % l)
+    # table gradients come out as views of one flat buffer
+    base = grads[0].data_ptr()
+    assert all(gr.data_ptr() == base + l * gr.numel() * 4 for l, gr in enumerate(grads))
+
+
+def test_hash_resolutions_and_coords(pn, golden):
+    g = golden("hash_primitives")
+    e512 = pn.HashEmbedder((torch.zeros(3), torch.ones(3)), log2_hashmap_size=4, finest_resolution=512).cuda()
+    e1024 = pn.HashEmbedder((torch.zeros(3), torch.ones(3)), log2_hashmap_size=4, finest_resolution=1024).cuda()
+    assert list(e512.grid().resolution) == list(g["res512"])
+    assert list(e1024.grid().resolution) == list(g["res1024"])
+    from indoor_nerf_b200 import utils
+    c = cu(g["corners"])
+    for k in (12, 19, 22):
+        assert (utils.hash(c, k).cpu().numpy() == g["h%d" % k]).all()
+    big = torch.randint(0, 1025, (4, 5, 6, 3), device="cuda")
+    assert (utils.hash(big, 19) == O.hash_coords(big, 19)).all()
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_hash_quant_golden(pn, golden, mode):
+    g = golden("hash_embed_quant_" + mode)
+    tables = synthetic_tables(16, 15, salt=5)
+    emb = embedder_from(pn, g["box_min"], g["box_max"], 15, 512, tables, use_quantization=True, quantization_bits=8)
+    rs = np.random.RandomState(11)
+    with torch.no_grad():
+        for q in emb.quantizers:
+            q.soft_bits.fill_(float(rs.uniform(3.2, 11.7)))
+    emb.current_step = 10_000
+    emb.train()
+    x = cu(g["x"])
+    feat_cal, _ = emb(x)                              # calibrates from the kernel's min/max pass
+    for l, q in enumerate(emb.quantizers):
+        st = g["q%d" % l]
+        got = [float(q.soft_bits), float(q.range_scale), float(q.v_max), float(q.running_min), float(q.running_max)]
+        assert got == [float(v) for v in st], "quantizer %d calibration" % l
+    assert (feat_cal.detach().cpu().numpy() == g["feat_first_call"]).all()
+    if mode == "eval":
+        emb.eval()
+    feat, keep = emb(x)
+    assert (feat.detach().cpu().numpy() == g["feat"]).all()
+    assert (keep.cpu().numpy() == g["keep"]).all()
+
+
+def test_hash_large_properties(pn):
+    """Full-size (T = 2^19, 2^22 points) checks that do not need the oracle: agreement with the oracle on a
+    slice, linearity in the tables, and sum(dE_l) == sum(dfeat_l) because trilinear weights sum to 1."""
+    P, log2T = 1 << 22, 19
+    box = (np.array([-3.0, -3.5, -2.0], np.float32), np.array([3.0, 3.5, 4.0], np.float32))
+    tables = synthetic_tables(16, log2T, salt=77)
+    emb = embedder_from(pn, box[0], box[1], log2T, 512, tables).eval()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(P, 3, device="cuda", generator=gen) * cu(box[1] - box[0]) + cu(box[0])
+    feat, keep = emb(x)
+    assert keep.all()
+    # oracle on the GPU for a slice
+    sl = slice(12345, 12345 + 65536)
+    res = O.level_resolutions(16, 512, device="cuda")
+    of, ok, oi = O.hash_embed(x[sl], cu(box[0]), cu(box[1]), [e.weight.detach() for e in emb.embeddings], res, log2T,
+                              return_indices=True)
+    assert (pn.ops.hash_indices(emb.grid(), x[sl]).long() == oi).all()
+    assert (feat[sl] == of).all()
+    # linearity
+    with torch.no_grad():
+        for e in emb.embeddings:
+            e.weight.mul_(2.0)
+    feat2, _ = emb(x)
+    assert (feat2 == 2.0 * feat).all()
+    # gradient mass conservation
+    dfeat = torch.randn(P, 32, device="cuda", generator=gen)
+    (feat2 * dfeat).sum().backward()
+    for l in (0, 5, 15):
+        got = emb.embeddings[l].weight.grad.double().sum(0)
+        want = dfeat[:, 2 * l:2 * l + 2].double().sum(0)
+        close(got, want, 1e-4, "grad mass level %d" % l)
+
+
+# ------------------------------------------------------------------------------------------------------
+# SH + K2
+# ------------------------------------------------------------------------------------------------------
+def test_sh(pn, golden):
+    g = golden("sh4")
+    out = pn.SHEncoder()(cu(g["dirs"]))
+    assert (out.cpu().numpy() == g["out"]).all()
+
+
+@pytest.mark.parametrize("tag", ["plain", "normals"])
+def test_mlp_golden(pn, golden, tag):
+    g = golden("nerf_small_" + tag)
+    w = {k[2:]: T(g[k]) for k in g.files if k.startswith("w_")}
+    m = mlp_from(pn, w)
+    x = cu(g["x"]).requires_grad_(True)
+    out = m(x)
+    close(out, g["out"], what="mlp out")
+    (out * cu(g["gout"])).sum().backward()
+    close(x.grad, g["gx"], what="mlp dx")
+    for k, gr in mlp_grads(m).items():
+        close(gr, g["g_" + k], what="mlp d" + k)
+
+
+def test_mlp_ragged_and_strided(pn):
+    """Tile tails (P not a multiple of 128), P = 1, and the dirs/keep entry against the [P,48] entry."""
+    w = mlp_weights(3)
+    m = mlp_from(pn, w)
+    wd = {k: v.cuda().contiguous() for k, v in w.items()}
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for P, S in ((1, 1), (127, 127), (129, 43), (1000, 8)):
+        feat = torch.randn(P, 32, device="cuda", generator=gen) * 0.3
+        dirs = torch.nn.functional.normalize(torch.randn(P // S, 3, device="cuda", generator=gen), dim=-1)
+        keep = torch.rand(P, device="cuda", generator=gen) > 0.3
+        sh = pn.ops.sh_encode(dirs).repeat_interleave(S, 0)
+        ref = O.nerf_small(torch.cat([feat, sh], -1), wd)
+        ref[~keep, -1] = 0
+        out = pn.ops.mlp_fwd(wd, feat, dirs=dirs, samples_per_ray=S, keep=keep)
+        close(out, ref, what="mlp dirs/keep P=%d" % P)
+        out2 = m(torch.cat([feat, sh], -1))
+        out2 = out2.clone(); out2[~keep, -1] = 0
+        close(out2, ref, what="mlp x48 P=%d" % P)
+
+
+def test_mlp_quant_golden(pn, golden):
+    g = golden("nerf_small_quant")
+    w = {k[2:]: T(g[k]) for k in g.files if k.startswith("w_") and k != "w_q"}
+    m = mlp_from(pn, w, use_quantization=True, quantization_bits=8).train()
+    x = cu(g["x"])
+    out = m(x)                                         # calibrates both quantisers
+    aq, wq = m.sigma_act_quantizers[0], m.sigma_weight_quantizer
+    assert float(wq.range_scale) == float(g["w_q"][1])
+    close(torch.stack([aq.range_scale.data, aq.v_max.data]), g["act_q"][1:], 1e-6, "act quantizer calibration")
+    close(out, g["out"], what="quantised mlp (train form)")
+    close(m.eval()(x), g["out_eval"], what="quantised mlp (eval form)")
+
+
+# ------------------------------------------------------------------------------------------------------
+# K3
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["s64", "s192n", "s128"])
+def test_composite_golden(pn, golden, tag):
+    g = golden("raw2outputs_" + tag)
+    raw = cu(g["raw"]).requires_grad_(True)
+    normals = raw.shape[-1] == 7
+    noise = cu(g["noise"]) if g["noise"].size else None
+    outs = pn.ops.CompositeFn.apply(raw, cu(g["z"]), cu(g["d"]), noise, bool(g["white"]))
+    for k, v in zip(["rgb", "disp", "acc", "weights", "depth", "sparsity"], outs):
+        close(v, g[k], what="composite " + k)
+    rgb, disp, acc, wts, depth, sp = outs[:6]
+    ok = torch.isfinite(depth)
+    loss = (rgb * cu(g["cot_rgb"])).sum() + (depth[ok] * cu(g["cot_depth"])[ok]).sum() + (acc * cu(g["cot_acc"])).sum() \
+        + (sp * cu(g["cot_sp"])).sum() + (wts * cu(g["cot_w"])).sum() + (disp[ok] * cu(g["cot_disp"])[ok]).sum()
+    if normals:
+        close(outs[6], g["normal"], what="normal map")
+        loss = loss + (outs[6] * cu(g["cot_normal"])).sum()
+    loss.backward()
+    close(raw.grad, g["graw"], what="composite draw")
+
+
+def test_composite_known(pn, golden):
+    g = golden("raw2outputs_known")
+    outs = pn.raw2outputs(cu(g["raw"]), cu(g["z"]), cu(g["d"]), 0, True)
+    for k, v in zip(["rgb", "disp", "acc", "weights", "depth", "sparsity"], outs):
+        close(v, g[k], what=k)
+
+
+def test_composite_unused_outputs_give_no_nan(pn):
+    """Only rgb in the loss (the reference's default training): empty rays (acc == 0, depth NaN) must not
+    poison the gradient — autograd never visits the depth branch, and neither do we."""
+    raw = torch.randn(8, 64, 4, device="cuda")
+    raw[0, :, 3] = -1.0
+    raw.requires_grad_(True)
+    z = torch.sort(2 + 4 * torch.rand(8, 64, device="cuda"), -1)[0]
+    d = torch.randn(8, 3, device="cuda")
+    rgb = pn.raw2outputs(raw, z, d, 0, True)[0]
+    rgb.sum().backward()
+    assert torch.isfinite(raw.grad).all()
+    raw_o = raw.detach().clone().requires_grad_(True)
+    O.raw2outputs(raw_o, z, d, None, True)[0].sum().backward()
+    close(raw.grad, raw_o.grad, what="rgb-only gradient")
+
+
+# ------------------------------------------------------------------------------------------------------
+# K4
+# ------------------------------------------------------------------------------------------------------
+def test_sample_pdf_golden(pn, golden):
+    g = golden("sample_pdf")
+    bins, w, u = cu(g["bins"]), cu(g["weights"]), cu(g["u"])
+    # (i) from a given cdf: bit-exact bins and samples
+    _, inds_o, cdf_o = O.sample_pdf(bins, w, 128, u=u, return_inds=True)
+    s, inds = pn.ops.sample_from_cdf(cdf_o, bins, u)
+    assert (inds.long() == inds_o).all(), "sample bins must be bit-exact"
+    assert (s == O.searchsorted_from_cdf(cdf_o, u, bins)[0]).all()
+    # (ii) whole op against the golden (CPU reference): any bin that differs must be an ulp-level tie
+    for u_in, key in ((u, "rnd"), (torch.linspace(0., 1., 128, device="cuda"), "det")):
+        s, inds, cdf = pn.ops.sample_pdf(bins, w, u_in, return_inds=True, return_cdf=True)
+        uu = u_in if u_in.dim() == 2 else u_in.expand(bins.shape[0], 128)
+        _, inds_ref, cdf_ref = O.sample_pdf(T(g["bins"]), T(g["weights"]), 128, u=uu.cpu(), return_inds=True)
+        close(cdf, cdf_ref, 1e-6, "cdf")
+        diff = (inds.cpu().long() != inds_ref)
+        if diff.any():
+            k = torch.minimum(inds.cpu().long(), inds_ref)[diff]
+            rows = diff.nonzero()[:, 0]
+            gap = (uu.cpu()[diff] - cdf_ref[rows, k]).abs()
+            assert (gap <= 4 * 1.2e-7).all(), "bin mismatch that is not a tie"
+        assert diff.float().mean() < 1e-3
+        same = ~diff
+        close(s.cpu()[same], T(g[key])[same], 1e-5, "samples " + key)
+    merged = pn.ops.sort_merge(cu(g["z"]), cu(g["rnd"]))
+    assert (merged.cpu().numpy() == g["merged"]).all()
+    k = golden("sample_pdf_known")
+    out = pn.sample_pdf(torch.tensor([[2., 3, 4, 5]]).cuda(), torch.tensor([[.1, .7, .2]]).cuda(), 5, det=True)
+    close(out, k["out"], 1e-6, "known sample_pdf")
+
+
+def test_sample_sort_large(pn):
+    """Full-size ray batch: sort_merge == torch.sort bit for bit; bins from our cdf == searchsorted on it."""
+    N = 65536
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    z = torch.sort(2 + 4 * torch.rand(N, 64, device="cuda", generator=gen), -1)[0]
+    w = torch.rand(N, 64, device="cuda", generator=gen) ** 6
+    u = torch.rand(N, 128, device="cuda", generator=gen)
+    mid = .5 * (z[:, 1:] + z[:, :-1])
+    s, inds, cdf = pn.ops.sample_pdf(mid, w[:, 1:-1], u, return_inds=True, return_cdf=True)
+    assert (inds.long() == torch.searchsorted(cdf, u, right=True)).all()
+    assert (s == O.searchsorted_from_cdf(cdf, u, mid)[0]).all()
+    merged = pn.ops.sort_merge(z, s)
+    assert (merged == torch.sort(torch.cat([z, s], -1), -1)[0]).all()
+    # against the oracle's own cdf: mismatching bins are rare and only at ulp-level ties
+    _, inds_o, cdf_o = O.sample_pdf(mid, w[:, 1:-1], 128, u=u, return_inds=True)
+    diff = inds.long() != inds_o
+    assert diff.float().mean() < 1e-4
+    if diff.any():
+        k = torch.minimum(inds.long(), inds_o)[diff]
+        rows = diff.nonzero()[:, 0]
+        assert ((u[diff] - cdf_o[rows, k]).abs() <= 8 * 1.2e-7).all()
+
+
+# ------------------------------------------------------------------------------------------------------
+# K5 + small pieces
+# ------------------------------------------------------------------------------------------------------
+def test_rays_golden(pn, golden):
+    g = golden("rays")
+    H, W = int(g["H"]), int(g["W"])
+    ro, rd = pn.get_rays(H, W, g["K"], T(g["c2w"]))
+    assert (rd.cpu().numpy() == g["rays_d"]).all() and (ro.cpu().numpy() == g["rays_o"]).all()
+    no, nd = pn.ndc_rays(H, W, float(g["K"][0][0]), 1., ro - torch.tensor([0, 0, 10.0], device="cuda"), rd)
+    assert (no.cpu().numpy() == g["ndc_o"]).all() and (nd.cpu().numpy() == g["ndc_d"]).all()
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole render_rays through the drop-in modules
+# ------------------------------------------------------------------------------------------------------
+class _Rng:
+    """Feeds the golden's random draws to torch.rand / torch.randn in call order."""
+
+    def __init__(self, rand, randn):
+        self.rand, self.randn = list(rand), list(randn)
+
+    def __enter__(self):
+        self._r, self._n = torch.rand, torch.randn
+        torch.rand = lambda *a, **k: self.rand.pop(0)
+        torch.randn = lambda *a, **k: self.randn.pop(0)
+
+    def __exit__(self, *a):
+        torch.rand, torch.randn = self._r, self._n
+
+
+@pytest.mark.parametrize("tag", ["blender", "det", "normals_noise"])
+def test_render_rays_golden(pn, golden, tag):
+    g = golden("render_rays_" + tag)
+    log2T = int(g["log2T"])
+    tables = synthetic_tables(16, log2T, amp=float(g["amp"]), salt=int(g["salt"]))
+    emb = embedder_from(pn, g["box_min"], g["box_max"], log2T, 512, tables).eval()
+    ws = [{k[3:]: T(g[k]) for k in g.files if k.startswith(p)} for p in ("w0_", "w1_")]
+    nets = [mlp_from(pn, w) for w in ws]
+    normals = "w0_n0w" in g.files
+    sh = pn.SHEncoder()
+    query = lambda inputs, viewdirs, fn: pn.run_network(inputs, viewdirs, fn, embed_fn=emb, embeddirs_fn=sh)
+    std, perturb, S_imp = float(g["raw_noise_std"]), float(g["perturb"]), int(g["N_importance"])
+    rand = [cu(g["t_rand"]), cu(g["u"])] if perturb > 0 else []
+    randn = [cu(g["noise0"]), cu(g["noise1"])] if std > 0 else []
+    with _Rng(rand, randn):
+        ret = pn.render_rays(cu(g["rays"]), nets[0], query, 64, embed_fn=emb, retraw=True, perturb=perturb,
+                             N_importance=S_imp, network_fine=nets[1], white_bkgd=bool(g["white"]),
+                             raw_noise_std=std, predict_normals=normals)
+    assert (ret["pts"].cpu().numpy() == g["pts"]).all(), "fine sample positions (=> bins, sort order) must be bit-exact"
+    for k in ["rgb_map", "depth_map", "acc_map", "sparsity_loss", "rgb0", "depth0", "acc0", "sparsity_loss0",
+              "z_std", "raw"] + (["normal_map", "normal0"] if normals else []):
+        close(ret[k], g[k], 2e-5, k)
+    target = cu(g["target"])
+    loss = ((ret["rgb_map"] - target) ** 2).mean() + ((ret["rgb0"] - target) ** 2).mean() \
+        + 1e-3 * (ret["sparsity_loss"].sum() + ret["sparsity_loss0"].sum())
+    close(loss, g["loss"], what="loss")
+    loss.backward()
+    close(torch.stack([e.weight.grad.abs().sum() for e in emb.embeddings]), g["g_table_abs_sum"], 1e-4, "table grads")
+    for i, m in enumerate(nets):
+        for k, gr in mlp_grads(m).items():
+            ref = g["g_m%d_%s" % (i, k)]
+            got = gr if gr is not None else torch.zeros(ref.shape)
+            close(got, ref, 1e-4, "net%d d%s" % (i, k))
+
+
+def test_render_against_oracle_on_gpu(pn):
+    """4096 rays, 64+128 samples, T=2^19: our drop-in modules vs the oracle executed on the GPU (i.e. the
+    reference's own ATen path on this device) with identical parameters and random draws."""
+    torch.manual_seed(0)
+    box = (np.array([-3.2, -3.1, -3.3], np.float32), np.array([3.1, 3.3, 3.2], np.float32))
+    log2T = 19
+    tables = synthetic_tables(16, log2T, amp=0.3, salt=9)
+    emb = embedder_from(pn, box[0], box[1], log2T, 512, tables).train()
+    ws = [mlp_weights(41), mlp_weights(42)]
+    nets = [mlp_from(pn, w) for w in ws]
+    N = 4096
+    rs = np.random.RandomState(2)
+    o = (rs.randn(N, 3) * 0.2 + np.array([0, 0, 4.0])).astype(np.float32)
+    d = (rs.randn(N, 3) * 0.8 - o).astype(np.float32)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    rays = cu(np.concatenate([o, d, np.full((N, 1), 2.0, np.float32), np.full((N, 1), 6.0, np.float32), d], -1))
+    t_rand, u = torch.rand(N, 64, device="cuda"), torch.rand(N, 128, device="cuda")
+    sh = pn.SHEncoder()
+    query = lambda inputs, viewdirs, fn: pn.run_network(inputs, viewdirs, fn, embed_fn=emb, embeddirs_fn=sh)
+    with _Rng([t_rand, u], []):
+        ret = pn.render_rays(rays, nets[0], query, 64, embed_fn=emb, retraw=True, perturb=1.0, N_importance=128,
+                             network_fine=nets[1], white_bkgd=True)
+    # oracle on the GPU
+    tabs = [e.weight.detach().clone().requires_grad_(True) for e in emb.embeddings]
+    wo = [{k: v.cuda().clone().requires_grad_(True) for k, v in w.items()} for w in ws]
+    res = O.level_resolutions(16, 512, device="cuda")
+    embed = lambda x: O.hash_embed(x, cu(box[0]), cu(box[1]), tabs, res, log2T)
+    q = [lambda pts, vd, w=w: O.run_network(pts, vd, embed, lambda x: O.nerf_small(x, w)) for w in wo]
+    ref = O.render_rays(rays, q[0], q[1], 64, 128, t_rand=t_rand, u=u, white_bkgd=True)
+    same = (ret["pts"] == ref["pts"]).all(-1).all(-1)
+    assert same.float().mean() > 0.999, "rays whose fine samples differ: %d" % int((~same).sum())
+    for k in ["rgb_map", "depth_map", "acc_map", "sparsity_loss", "rgb0", "acc0", "raw"]:
+        close(ret[k][same], ref[k][same], 5e-5, k)
+    target = torch.rand(N, 3, device="cuda")
+    lo = lambda r: ((r["rgb_map"][same] - target[same]) ** 2).mean() + ((r["rgb0"][same] - target[same]) ** 2).mean() \
+        + 1e-4 * (r["sparsity_loss"][same].sum() + r["sparsity_loss0"][same].sum())
+    lo(ret).backward()
+    lo(ref).backward()
+    for l in (0, 4, 9, 15):
+        close(emb.embeddings[l].weight.grad, tabs[l].grad, 1e-4, "table grad level %d" % l)
+    for i, m in enumerate(nets):
+        for k, gr in mlp_grads(m).items():
+            close(gr, wo[i][k].grad, 1e-4, "net%d d%s" % (i, k))
+
+
+def test_full_frame_render_shapes(pn):
+    """render(c2w=...) on a small frame: list structure and shapes of the reference (run_nerf.py:148-151)."""
+    box = (torch.tensor([-3.0] * 3), torch.tensor([3.0] * 3))
+    emb = pn.HashEmbedder(box, log2_hashmap_size=14).cuda().eval()
+    net = mlp_from(pn, mlp_weights(1)).eval()
+    sh = pn.SHEncoder()
+    H = W = 40
+    K = np.array([[50.0, 0, 20], [0, 50.0, 20], [0, 0, 1]])
+    c2w = torch.tensor([[1.0, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 4.0]])
+    query = lambda inputs, viewdirs, fn: pn.run_network(inputs, viewdirs, fn, embed_fn=emb, embeddirs_fn=sh)
+    with torch.no_grad():
+        rgb, depth, acc, extras = pn.render(H, W, K, chunk=1000, c2w=c2w, ndc=False, near=2., far=6.,
+                                            use_viewdirs=True, network_fn=net, network_query_fn=query, N_samples=64,
+                                            N_importance=128, network_fine=net, embed_fn=emb, white_bkgd=True)
+    assert rgb.shape == (H, W, 3) and depth.shape == (H, W) and acc.shape == (H, W)
+    assert set(extras) >= {"sparsity_loss", "pts", "rays_d", "rgb0", "depth0", "acc0", "sparsity_loss0", "z_std"}
+    assert extras["pts"].shape == (H, W, 192, 3)
+    assert torch.isfinite(rgb).all()

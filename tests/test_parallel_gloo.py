@@ -1,0 +1,138 @@
+"""Data-parallel host logic on CPU: two gloo ranks.  Checks that (a) the flat table-gradient buffer and the
+packed MLP gradients are summed across ranks in place, (b) the loss scaling in Trainer.losses makes the SUM of
+the ranks' gradients equal the single-process gradient over the concatenated batch, (c) ray sharding and
+pixel-row sharding cover the work exactly once, (d) parameters / quantiser calibration are made consistent."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, fn_name, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = globals()[fn_name](rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn_name, world=2):
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, fn_name, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def _models():
+    import indoor_nerf_b200 as pn
+    torch.manual_seed(0)
+    emb = pn.HashEmbedder((torch.tensor([-1.0] * 3), torch.tensor([1.0] * 3)), log2_hashmap_size=6)
+    net = pn.NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, input_ch=32, input_ch_views=16)
+    return emb, net
+
+
+def _allreduce(rank, world):
+    from indoor_nerf_b200 import parallel
+    emb, net = _models()
+    flat = torch.full((16, 64, 2), float(rank + 1))
+    for l, e in enumerate(emb.embeddings):
+        e.weight.grad = flat[l]                        # views of one buffer, as the backward kernel leaves them
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    got = parallel.flat_table_grad(emb)
+    assert got.data_ptr() == flat.data_ptr()           # zero-copy re-assembly
+    parallel.allreduce_gradients(emb, [net], None)
+    ok = bool((flat == 3.0).all()) and all(bool((p.grad == 3.0 * (i + 1)).all()) for i, p in enumerate(net.parameters()))
+    # non-flat grads are packed and re-pointed
+    for e in emb.embeddings:
+        e.weight.grad = torch.full((64, 2), float(rank + 1))
+    parallel.allreduce_gradients(emb, [net], None)
+    ok = ok and all(bool((e.weight.grad == 3.0).all()) for e in emb.embeddings)
+    g0 = emb.embeddings[0].weight.grad
+    ok = ok and all(e.weight.grad.data_ptr() == g0.data_ptr() + l * 128 * 4 for l, e in enumerate(emb.embeddings))
+    return ok
+
+
+def _loss_scaling(rank, world):
+    """Linear model stand-in for the renderer: gradient of the scaled per-rank losses, summed, must equal the
+    gradient of the reference loss on the whole batch."""
+    from indoor_nerf_b200 import parallel
+    torch.manual_seed(1)
+    N = 10
+    x, tgt = torch.randn(N, 3), torch.randn(N, 3)
+    w_full = torch.ones(3, requires_grad=True)
+    full = torch.mean((x * w_full - tgt) ** 2) + 1e-3 * (x * w_full).abs().sum()
+    full.backward()
+    rays = torch.stack([x, x])
+    rs, ts = parallel.shard_rays(rays, tgt, rank, world)
+    w = torch.ones(3, requires_grad=True)
+    # equal shards: mean over the shard / world == contribution to the global mean
+    loss = torch.mean((rs[0] * w - ts) ** 2) / world + 1e-3 * (rs[0] * w).abs().sum()
+    loss.backward()
+    dist.all_reduce(w.grad)
+    return bool(torch.allclose(w.grad, w_full.grad, rtol=1e-6)), int(rs.shape[1])
+
+
+def _render_shards(rank, world):
+    from indoor_nerf_b200 import parallel
+    H, W = 7, 5
+    o = torch.arange(H * W * 3, dtype=torch.float32).reshape(H, W, 3)
+
+    def fake_render(H_, W_, rays=None, **kw):
+        ro, rd = rays
+        return [ro * 2.0, ro[..., 0] + 1.0, rd[..., 1]]
+    rgb, depth, acc = parallel.render_sharded(fake_render, H, W, o, o, None, gather=True)
+    return bool(torch.equal(rgb, o * 2.0) and torch.equal(depth, o[..., 0] + 1.0) and torch.equal(acc, o[..., 1]))
+
+
+def _broadcast_and_calibration(rank, world):
+    import indoor_nerf_b200 as pn
+    from indoor_nerf_b200 import parallel
+    emb, net = _models()
+    with torch.no_grad():
+        emb.table_storage.fill_(float(rank))
+        for p in net.parameters():
+            p.fill_(float(rank))
+    parallel.broadcast_parameters([emb, net], src=1)
+    ok = bool((emb.table_storage == 1.0).all()) and all(bool((p == 1.0).all()) for p in net.parameters())
+    q = pn.LearnedBitwidthQuantizer(symmetric=False)
+    q.calibrate_minmax(torch.tensor(-1.0 - rank), torch.tensor(2.0 + rank))
+    parallel.sync_quantizer_calibration([q])
+    ok = ok and float(q.running_min) == -2.0 and float(q.running_max) == 3.0 and float(q.range_scale) == 5.0
+    return ok
+
+
+def test_allreduce_gradients():
+    assert all(_run("_allreduce"))
+
+
+def test_loss_scaling_sums_to_global_gradient():
+    res = _run("_loss_scaling")
+    assert all(r[0] for r in res) and sum(r[1] for r in res) == 10
+
+
+def test_pixel_sharded_render_gathers_full_frame():
+    assert all(_run("_render_shards"))
+
+
+def test_broadcast_and_quantizer_sync():
+    assert all(_run("_broadcast_and_calibration"))
+
+
+def test_shard_helpers_cover_everything():
+    from indoor_nerf_b200 import parallel
+    rays, tgt = torch.arange(2 * 11 * 3.).reshape(2, 11, 3), torch.arange(33.).reshape(11, 3)
+    for world in (1, 2, 4, 8):
+        parts = [parallel.shard_rays(rays, tgt, r, world) for r in range(world)]
+        assert torch.equal(torch.cat([p[0] for p in parts], 1), rays)
+        assert torch.equal(torch.cat([p[1] for p in parts], 0), tgt)
+        rows = [parallel.pixel_rows(800, r, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == 800 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
