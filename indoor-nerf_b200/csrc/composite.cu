@@ -114,7 +114,7 @@ composite_fwd_kernel(const float *__restrict__ raw, int C, const float *__restri
       if (white) { const float bg = 1.0f - sw; c0 += bg; c1 += bg; c2 += bg; }   // :398
       if (rgb) { rgb[3 * r + 0] = c0; rgb[3 * r + 1] = c1; rgb[3 * r + 2] = c2; }
       if (depth) depth[r] = dep;
-      if (disp) disp[r] = 1.0f / fmaxf(1e-10f, dep);                // :394
+      if (disp) disp[r] = (dep != dep) ? dep : 1.0f / fmaxf(1e-10f, dep);   // :394 (torch.max propagates NaN)
       if (acc) acc[r] = sw;
       if (sparsity) sparsity[r] = h;
       if (C == 7 && normal) {
