@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 3
+#define PN_ABI_VERSION 4
 #define PN_MAX_LEVELS 16
 
 #define PN_EINVAL (-1)   /* bad argument */
@@ -144,6 +144,19 @@ int pn_mlp_fwd(const pn_mlp_weights *w, const pn_mlp_input *in, float *out, pn_s
 int pn_mlp_bwd(const pn_mlp_weights *w, const pn_mlp_input *in, const float *dout, float *dfeat,
                int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads *dw,
                pn_stream_t stream);
+
+/* The same two operations in the bf16 tensor-core mode (tcgen05.mma with TMEM accumulators: inputs,
+ * weights and hidden activations rounded to bf16, fp32 accumulation, fp32 outputs and gradients).  Same
+ * arguments, same semantics; results agree with the fp32 mode to ~2e-3 relative (BASELINE north_star). */
+int pn_mlp_fwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, float *out, pn_stream_t stream);
+int pn_mlp_bwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, const float *dout, float *dfeat,
+                    int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads *dw,
+                    pn_stream_t stream);
+
+/* Diagnostic: one tcgen05 GEMM with caller-chosen shared-memory descriptor fields (cfg[15], see
+ * mlp_tc.cu) — proves the K-major / MN-major operand readings and the TMEM accumulator layouts on the
+ * hardware.  D is the raw [128 lanes][N] accumulator. */
+int pn_tc_selftest(const int32_t *cfg, const float *A, const float *B, float *D, pn_stream_t stream);
 
 /* ---- volume rendering ---------------------------------------------------------------------------- */
 

@@ -3,6 +3,7 @@
 reference's Python API.  Import as ``indoor_nerf_b200`` (the importable alias of this directory)."""
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401
+from .ops import get_mlp_mode, set_mlp_mode  # noqa: F401
 from .hash_encoding import HashEmbedder, SHEncoder  # noqa: F401
 from .quantization import FakeQuantizer, LearnedBitwidthQuantizer, PassthroughQuantizer, calculate_fqr  # noqa: F401
 from .run_nerf_helpers import (NeRFSmall, get_embedder, get_rays, get_rays_np, img2mse, mse2psnr, ndc_rays,  # noqa: F401

@@ -540,7 +540,7 @@ mlp_bwd_kernel(const MlpArgs A, const float *__restrict__ dout, float *__restric
   }
 }
 
-static int check_mlp(const pn_mlp_weights *w, const pn_mlp_input *in, bool *normals) {
+int check_mlp_args(const pn_mlp_weights *w, const pn_mlp_input *in, bool *normals) {
   PN_REQUIRE(w && in, PN_EINVAL, "NULL argument");
   PN_REQUIRE(w->s0 && w->s1 && w->c0 && w->c1 && w->c2, PN_EINVAL, "NULL weight pointer");
   const int n_normal = (w->n0w != nullptr) + (w->n0b != nullptr) + (w->n2w != nullptr) + (w->n2b != nullptr);
@@ -567,7 +567,7 @@ using namespace pn;
 
 extern "C" int pn_mlp_fwd(const pn_mlp_weights *w, const pn_mlp_input *in, float *out, pn_stream_t stream) {
   bool normals = false;
-  if (int e = check_mlp(w, in, &normals)) return e;
+  if (int e = check_mlp_args(w, in, &normals)) return e;
   PN_REQUIRE(out != nullptr, PN_EINVAL, "out is NULL");
   if (in->n_points == 0) return 0;
   MlpArgs A;
@@ -594,7 +594,7 @@ extern "C" int pn_mlp_bwd(const pn_mlp_weights *w, const pn_mlp_input *in, const
                           int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads *dw,
                           pn_stream_t stream) {
   bool normals = false;
-  if (int e = check_mlp(w, in, &normals)) return e;
+  if (int e = check_mlp_args(w, in, &normals)) return e;
   PN_REQUIRE(dout && dfeat && dw, PN_EINVAL, "NULL pointer argument");
   PN_REQUIRE(dfeat_stride >= 32 && dfeat_stride % 4 == 0 && ((uintptr_t)dfeat & 15) == 0, PN_EINVAL,
              "dfeat stride/alignment");

@@ -1,0 +1,692 @@
+// K2 / K2b (bf16 tensor-core mode) — NeRFSmall on tcgen05 with TMEM accumulators.
+//   thread = point = TMEM lane; a CTA owns a tile of 128 points; every layer is a 128 x N x K UMMA whose
+//   A operand (the previous layer's activations, bf16) and B operand (the weights, bf16) sit in shared
+//   memory in the tile layout of tc_common.cuh; the epilogue of each layer (tcgen05.ld -> ReLU -> bf16 ->
+//   st.shared) produces the next layer's A operand.  Nothing but the tile's inputs and outputs touches HBM.
+#include "hash_core.cuh"
+#include "tc_common.cuh"
+
+namespace pn {
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------------
+// Descriptor self-test: D = A(.)B with host-chosen descriptor fields, so that the K-major / MN-major
+// readings of the tile layout and the M=64 / M=128 accumulator layouts are proven on hardware, not assumed.
+// ------------------------------------------------------------------------------------------------------
+struct SelfTestArgs {
+  int ra, ca, rb, cb;              // tile shapes (rows, cols) of the two operands as stored
+  int M, N, ksteps;                // instruction shape and number of K=16 steps
+  int a_mn, b_mn;                  // 1 = read the operand MN-major
+  uint32_t lbo_a, sbo_a, adv_a;    // descriptor fields (bytes) and per-k-step start-address advance
+  uint32_t lbo_b, sbo_b, adv_b;
+};
+
+__global__ void __launch_bounds__(128) tc_selftest_kernel(SelfTestArgs a, const float *__restrict__ A,
+                                                           const float *__restrict__ B, float *__restrict__ D) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar;
+  uint8_t *ta = smem;
+  uint8_t *tb = smem + ((a.ra * a.ca * 2 + 127) / 128) * 128;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int i = t; i < a.ra * (a.ca / 8); i += 128) {
+    const int r = i / (a.ca / 8), c8 = i % (a.ca / 8);
+    float v[8];
+    for (int j = 0; j < 8; ++j) v[j] = A[r * a.ca + c8 * 8 + j];
+    st_chunk(ta, chunk_off(r, c8, a.ca / 8), v);
+  }
+  for (int i = t; i < a.rb * (a.cb / 8); i += 128) {
+    const int r = i / (a.cb / 8), c8 = i % (a.cb / 8);
+    float v[8];
+    for (int j = 0; j < 8; ++j) v[j] = B[r * a.cb + c8 * 8 + j];
+    st_chunk(tb, chunk_off(r, c8, a.cb / 8), v);
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 64);
+  if (t == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (t == 0) {
+    const uint32_t idesc = instr_desc(a.M, a.N, a.a_mn, a.b_mn);
+    for (int k = 0; k < a.ksteps; ++k) {
+      const uint64_t da = smem_desc(smem_u32(ta) + k * a.adv_a, a.lbo_a, a.sbo_a);
+      const uint64_t db = smem_desc(smem_u32(tb) + k * a.adv_b, a.lbo_b, a.sbo_b);
+      mma_f16(tmem, da, db, idesc, k > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+  for (int c = 0; c < a.N; c += 16) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[t * a.N + c + j] = v[j];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// NeRFSmall on the tensor cores
+// ------------------------------------------------------------------------------------------------------
+constexpr int kTcTile = 128;     // points per CTA tile = TMEM lanes = threads
+
+// shared-memory map (bytes).  All tiles in the tile layout of tc_common.cuh.
+struct TS {
+  static constexpr int W_S0 = 0;                  // [64 x 32]
+  static constexpr int W_S1 = W_S0 + 64 * 32 * 2; // [16 x 64]
+  static constexpr int W_C0 = W_S1 + 16 * 64 * 2; // [64 x 32] (col 31 = 0)
+  static constexpr int W_C1 = W_C0 + 64 * 32 * 2; // [64 x 64]
+  static constexpr int W_C2 = W_C1 + 64 * 64 * 2; // [16 x 64] (rows 3.. = 0)
+  static constexpr int W_N0 = W_C2 + 16 * 64 * 2; // [32 x 16] (col 15 = 0)
+  static constexpr int W_N2 = W_N0 + 32 * 16 * 2; // [16 x 32] (rows 3.. = 0)
+  static constexpr int BIAS = W_N2 + 16 * 32 * 2; // fp32: n0b[32], n2b[4]
+  static constexpr int A0 = BIAS + 256;           // [128 x 32] hash features (bias block padded to 256 B)
+  static constexpr int A1 = A0 + 128 * 32 * 2;    // [128 x 64] hidden (fwd: reused by every 64-wide layer; bwd: H1)
+  static constexpr int CIN = A1 + 128 * 64 * 2;   // [128 x 32] [sh16, geo15, 0]
+  static constexpr int NH = CIN + 128 * 32 * 2;   // [128 x 32] normal-head hidden
+  static constexpr int FWD_END = NH + 128 * 32 * 2;
+  // backward only
+  static constexpr int A1C = FWD_END;             // [128 x 64] colour hidden 1 -> its pre-activation grad
+  static constexpr int A2C = A1C + 128 * 64 * 2;  // [128 x 64] colour hidden 2 -> its pre-activation grad
+  static constexpr int DOUT = A2C + 128 * 64 * 2; // [128 x 16] (drgb, 0...)
+  static constexpr int DH2 = DOUT + 128 * 16 * 2; // [128 x 16] (dsigma, dgeo)
+  static constexpr int DNR = DH2 + 128 * 16 * 2;  // [128 x 16] (d raw normal, 0...)
+  static constexpr int BWD_END = DNR + 128 * 16 * 2;
+};
+static_assert(TS::A0 % 128 == 0 && TS::A1 % 128 == 0 && TS::CIN % 128 == 0 && TS::A1C % 128 == 0, "tile alignment");
+
+// TMEM columns
+constexpr uint32_t TM_D1 = 0;      // 64 columns: 64-wide layer outputs / input gradients
+constexpr uint32_t TM_D2 = 64;     // 32 columns: 16-wide outputs (sigma+geo, rgb, raw normal, dgeo from the normal head)
+constexpr uint32_t TM_DN = 64;     // normal-head hidden / its gradient: aliases D2 (never live in the same round)
+constexpr uint32_t TM_FWD_COLS = 128;
+constexpr uint32_t TM_GC1 = 96;    // wgrad accumulators (M = 64 layout: row m -> lane m%16 + 32*(m/16)), live across tiles
+constexpr uint32_t TM_GS0 = 160;
+constexpr uint32_t TM_GC0 = 192;
+constexpr uint32_t TM_GS1 = 224;   // [64 x 16] = dS1^T
+constexpr uint32_t TM_GC2 = 240;   // [64 x 16] = dC2^T
+constexpr uint32_t TM_BWD_COLS = 256;
+
+struct TcArgs {
+  pn_mlp_weights w;
+  pn_mlp_input in;
+  int normals;
+  int C;
+};
+
+// fp32 [N x K] row-major global weight (ld = Kvalid) -> bf16 tile [NT x KT], zero padded
+__device__ void load_w_tile(uint8_t *tile, const float *__restrict__ W, int NT, int KT, int Nvalid, int Kvalid) {
+  const int C8 = KT / 8;
+  for (int i = threadIdx.x; i < NT * C8; i += blockDim.x) {
+    const int r = i / C8, c8 = i - r * C8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      v[j] = (r < Nvalid && c < Kvalid) ? __ldg(W + r * Kvalid + c) : 0.f;
+    }
+    st_chunk(tile, chunk_off(r, c8, C8), v);
+  }
+}
+
+__device__ void load_all_weights(uint8_t *sm, const TcArgs &A) {
+  load_w_tile(sm + TS::W_S0, A.w.s0, 64, 32, 64, 32);
+  load_w_tile(sm + TS::W_S1, A.w.s1, 16, 64, 16, 64);
+  load_w_tile(sm + TS::W_C0, A.w.c0, 64, 32, 64, 31);
+  load_w_tile(sm + TS::W_C1, A.w.c1, 64, 64, 64, 64);
+  load_w_tile(sm + TS::W_C2, A.w.c2, 16, 64, 3, 64);
+  float *bias = reinterpret_cast<float *>(sm + TS::BIAS);
+  if (A.normals) {
+    load_w_tile(sm + TS::W_N0, A.w.n0w, 32, 16, 32, 15);
+    load_w_tile(sm + TS::W_N2, A.w.n2w, 16, 32, 3, 32);
+    for (int i = threadIdx.x; i < 36; i += blockDim.x)
+      bias[i] = (i < 32) ? __ldg(A.w.n0b + i) : (i < 35 ? __ldg(A.w.n2b + (i - 32)) : 0.f);
+  }
+}
+
+// operand descriptors of a tile: K-major (c = K) or MN-major (r = K)
+struct Opnd {
+  uint32_t addr, lbo, sbo, adv;
+};
+__device__ __forceinline__ Opnd k_major(const uint8_t *tile, int cols, int col0 = 0) {
+  return Opnd{smem_u32(tile) + (uint32_t)(col0 / 8) * 128u, 128u, (uint32_t)(cols / 8) * 128u, 256u};
+}
+__device__ __forceinline__ Opnd mn_major(const uint8_t *tile, int cols) {
+  const uint32_t rg = (uint32_t)(cols / 8) * 128u;
+  return Opnd{smem_u32(tile), rg, 128u, 2u * rg};
+}
+__device__ __forceinline__ void issue(uint32_t d, const Opnd &a, const Opnd &b, uint32_t idesc, int ksteps, bool accumulate) {
+  for (int k = 0; k < ksteps; ++k)
+    mma_f16(d, smem_desc(a.addr + k * a.adv, a.lbo, a.sbo), smem_desc(b.addr + k * b.adv, b.lbo, b.sbo), idesc,
+            (accumulate || k > 0) ? 1u : 0u);
+}
+
+// tile inputs: features -> A0, SH -> CIN[0..16)
+__device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, int64_t base, int p, bool valid) {
+  float v[8];
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    if (valid) {
+      const float4 *src = reinterpret_cast<const float4 *>(A.in.feat + (base + p) * A.in.feat_stride + c8 * 8);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    st_chunk(sm + TS::A0, chunk_off(p, c8, 4), v);
+  }
+  float o[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = 0.f;
+  if (valid) {
+    if (A.in.sh) {
+      const float4 *src = reinterpret_cast<const float4 *>(A.in.sh + (base + p) * A.in.sh_stride);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = __ldg(src + q);
+        o[4 * q] = a.x; o[4 * q + 1] = a.y; o[4 * q + 2] = a.z; o[4 * q + 3] = a.w;
+      }
+    } else {
+      const int64_t r = (base + p) / A.in.samples_per_ray;
+      sh4(__ldg(A.in.dirs + 3 * r), __ldg(A.in.dirs + 3 * r + 1), __ldg(A.in.dirs + 3 * r + 2), o);
+    }
+  }
+  st_chunk(sm + TS::CIN, chunk_off(p, 0, 4), o);
+  st_chunk(sm + TS::CIN, chunk_off(p, 1, 4), o + 8);
+}
+
+// epilogue of a 64-wide hidden layer: TMEM -> ReLU -> (fake-quant) -> bf16 tile row; returns the ReLU mask
+__device__ __forceinline__ uint64_t epi_hidden64(uint32_t taddr, uint8_t *tile, int p, const float *qrow) {
+  uint64_t mask = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float v[32];
+    tmem_ld16(taddr + h * 32, v);
+    tmem_ld16(taddr + h * 32 + 16, v + 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const bool pos = v[j] > 0.f;
+      if (pos) mask |= (1ull << (h * 32 + j));
+      v[j] = pos ? v[j] : 0.f;
+      if (qrow) v[j] = fake_quant(v[j], qrow[0], qrow[1], qrow[2], qrow[3], qrow[4], qrow[6] != 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st_chunk(tile, chunk_off(p, h * 4 + c, 8), v + 8 * c);
+  }
+  return mask;
+}
+
+// forward rounds shared by the forward kernel and the backward's recompute.
+// BWD = false: every 64-wide activation goes to A1.   BWD = true: H1 -> A1, colour hidden 1 -> A1C, 2 -> A2C.
+template <bool BWD>
+__device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_t tmem, uint64_t *bar, uint32_t &ph,
+                                           int p, int warp, const float *qrow, float &sigma, float nraw[3],
+                                           uint64_t &h1_mask) {
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const bool t0 = threadIdx.x == 0;
+  uint8_t *a1c = BWD ? sm + TS::A1C : sm + TS::A1;
+  uint8_t *a2c = BWD ? sm + TS::A2C : sm + TS::A1;
+  // R1: H1 = relu(X S0^T)
+  if (t0) {
+    fence_after_sync();
+    issue(tmem + TM_D1, k_major(sm + TS::A0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
+  h1_mask = epi_hidden64(lane_addr + TM_D1, sm + TS::A1, p, qrow);
+  fence_async_smem(); fence_before_sync(); __syncthreads();
+  // R2: [sigma, geo] = H1 S1^T
+  if (t0) {
+    fence_after_sync();
+    issue(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
+  {
+    float v[17];
+    tmem_ld16(lane_addr + TM_D2, v);
+    tmem_ld_wait();
+    sigma = v[0];
+    v[16] = 0.f;
+    st_chunk(sm + TS::CIN, chunk_off(p, 2, 4), v + 1);      // geo 0..7
+    st_chunk(sm + TS::CIN, chunk_off(p, 3, 4), v + 9);      // geo 8..14, 0
+  }
+  fence_async_smem(); fence_before_sync(); __syncthreads();
+  // R3: A1c = relu(CIN C0^T);  NH = relu(geo N0^T + b)
+  if (t0) {
+    fence_after_sync();
+    issue(tmem + TM_D1, k_major(sm + TS::CIN, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
+    if (A.normals)
+      issue(tmem + TM_DN, k_major(sm + TS::CIN, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
+  epi_hidden64(lane_addr + TM_D1, a1c, p, nullptr);
+  if (A.normals) {
+    const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS);
+    float v[32];
+    tmem_ld16(lane_addr + TM_DN, v);
+    tmem_ld16(lane_addr + TM_DN + 16, v + 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bias[j], 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st_chunk(sm + TS::NH, chunk_off(p, c, 4), v + 8 * c);
+  }
+  fence_async_smem(); fence_before_sync(); __syncthreads();
+  // R4: A2c = relu(A1c C1^T);  raw normal = NH N2^T + b
+  if (t0) {
+    fence_after_sync();
+    issue(tmem + TM_D1, k_major(a1c, 64), k_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 0), 4, false);
+    if (A.normals)
+      issue(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false);
+    mma_commit(bar);
+  }
+  mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
+  if (A.normals) {
+    const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + 32;
+    float v[16];
+    tmem_ld16(lane_addr + TM_D2, v);
+    tmem_ld_wait();
+    nraw[0] = v[0] + bias[0]; nraw[1] = v[1] + bias[1]; nraw[2] = v[2] + bias[2];
+  }
+  epi_hidden64(lane_addr + TM_D1, a2c, p, nullptr);
+  fence_async_smem(); fence_before_sync(); __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTcTile) mlp_tc_fwd_kernel(const TcArgs A, float *__restrict__ out) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar;
+  const int p = threadIdx.x, warp = p >> 5;
+  load_all_weights(sm, A);
+  if (warp == 0) tmem_alloc(&tmem_slot, TM_FWD_COLS);
+  if (p == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t ph = 0;
+  float q[8];
+  const float *qrow = nullptr;
+  if (A.in.act_q) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
+    if (q[5] != 0.f) qrow = q;
+  }
+  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kTcTile;
+    const bool valid = base + p < A.in.n_points;
+    tc_load_inputs(sm, A, base, p, valid);
+    fence_async_smem(); fence_before_sync(); __syncthreads();
+    float sigma, nraw[3] = {0.f, 0.f, 0.f};
+    uint64_t m;
+    tc_forward<false>(sm, A, tmem, &bar, ph, p, warp, qrow, sigma, nraw, m);
+    // R5: rgb = A2c C2^T
+    if (p == 0) {
+      fence_after_sync();
+      issue(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_C2, 64), instr_desc(128, 16, 0, 0), 4, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    float v[16];
+    tmem_ld16(lane_addr + TM_D2, v);
+    tmem_ld_wait();
+    if (valid) {
+      const bool kept = A.in.keep ? (A.in.keep[base + p] != 0) : true;
+      float *o = out + (base + p) * A.C;
+      if (A.C == 4) {
+        *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], kept ? sigma : 0.f);
+      } else {
+        const float nn = fmaxf(sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]), 1e-12f);
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = sigma;
+        o[4] = nraw[0] / nn; o[5] = nraw[1] / nn; o[6] = kept ? nraw[2] / nn : 0.f;
+      }
+    }
+    fence_before_sync(); __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc(tmem, TM_FWD_COLS);
+}
+
+
+// masked in-place epilogue of an input-gradient GEMM: tile row <- D * [tile row > 0] (or an explicit mask)
+__device__ __forceinline__ void epi_grad64(uint32_t taddr, uint8_t *tile, int p, bool use_mask, uint64_t mask) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float v[32];
+    tmem_ld16(taddr + h * 32, v);
+    tmem_ld16(taddr + h * 32 + 16, v + 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t off = chunk_off(p, h * 4 + c, 8);
+      if (use_mask) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * c + j] = ((mask >> (h * 32 + c * 8 + j)) & 1ull) ? v[8 * c + j] : 0.f;
+      } else {
+        float a[8];
+        ld_chunk(tile, off, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * c + j] = a[j] > 0.f ? v[8 * c + j] : 0.f;
+      }
+      st_chunk(tile, off, v + 8 * c);
+    }
+  }
+}
+
+__device__ __forceinline__ float tile_elem(const uint8_t *tile, int r, int c, int C8) {
+  const uint16_t h = *reinterpret_cast<const uint16_t *>(tile + chunk_off(r, c >> 3, C8) + (c & 7) * 2);
+  return __uint_as_float((uint32_t)h << 16);
+}
+
+// accumulator rows held by this thread (M = 64 layout): valid when lane < 16, row = 16*warp + lane
+__device__ __forceinline__ void flush_acc(uint32_t taddr, int ncols, bool owner, int row, float *dst, int pitch,
+                                          int row_valid, int col_valid, bool transposed) {
+  for (int c = 0; c < ncols; c += 16) {
+    float v[16];
+    tmem_ld16(taddr + c, v);
+    tmem_ld_wait();
+    if (owner && dst && row < row_valid) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c + j;
+        if (col < col_valid) atomicAdd(transposed ? dst + col * pitch + row : dst + row * pitch + col, v[j]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTcTile)
+mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restrict__ dfeat, int64_t dfeat_stride,
+                  float *__restrict__ dsh, int64_t dsh_stride, const pn_mlp_grads G) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar;
+  const int p = threadIdx.x, warp = p >> 5, lane = p & 31;
+  load_all_weights(sm, A);
+  if (warp == 0) tmem_alloc(&tmem_slot, TM_BWD_COLS);
+  if (p == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t ph = 0;
+  float q[8];
+  const float *qrow = nullptr;
+  if (A.in.act_q) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
+    if (q[5] != 0.f) qrow = q;
+  }
+  // normal-head weight gradients are reduced on the CUDA cores (tiny: 611 numbers), fp32 registers across tiles
+  float g_n2 = 0.f, g_n0[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool t0 = p == 0;
+  bool first = true;
+  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kTcTile;
+    const bool valid = base + p < A.in.n_points;
+    tc_load_inputs(sm, A, base, p, valid);
+    float d_o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      for (int c = 0; c < A.C; ++c) d_o[c] = __ldg(dout + (base + p) * A.C + c);
+      if (A.in.keep && A.in.keep[base + p] == 0) d_o[A.C - 1] = 0.f;            // run_nerf.py:66
+    }
+    fence_async_smem(); fence_before_sync(); __syncthreads();
+    float sigma, nraw[3] = {0.f, 0.f, 0.f};
+    uint64_t h1_mask;
+    tc_forward<true>(sm, A, tmem, &bar, ph, p, warp, qrow, sigma, nraw, h1_mask);
+
+    // B0: cotangent tiles
+    {
+      float v[8] = {d_o[0], d_o[1], d_o[2], 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      st_chunk(sm + TS::DOUT, chunk_off(p, 0, 2), v);
+      st_chunk(sm + TS::DOUT, chunk_off(p, 1, 2), z);
+      if (A.normals) {
+        const float nn = sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]);
+        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (nn > 1e-12f) {
+          const float m0 = nraw[0] / nn, m1 = nraw[1] / nn, m2 = nraw[2] / nn;
+          const float dot = m0 * d_o[4] + m1 * d_o[5] + m2 * d_o[6];
+          r[0] = (d_o[4] - m0 * dot) / nn; r[1] = (d_o[5] - m1 * dot) / nn; r[2] = (d_o[6] - m2 * dot) / nn;
+        } else {
+          r[0] = d_o[4] / 1e-12f; r[1] = d_o[5] / 1e-12f; r[2] = d_o[6] / 1e-12f;
+        }
+        st_chunk(sm + TS::DNR, chunk_off(p, 0, 2), r);
+        st_chunk(sm + TS::DNR, chunk_off(p, 1, 2), z);
+      }
+    }
+    fence_async_smem(); fence_before_sync(); __syncthreads();
+    // B1: dC2^T += A2c^T dOut ; dA2 = dOut C2 ; (normals) dNH = dNraw N2
+    if (t0) {
+      fence_after_sync();
+      issue(tmem + TM_GC2, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::DOUT, 16), instr_desc(64, 16, 1, 1), 8, !first);
+      issue(tmem + TM_D1, k_major(sm + TS::DOUT, 16), mn_major(sm + TS::W_C2, 64), instr_desc(128, 64, 0, 1), 1, false);
+      if (A.normals)
+        issue(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false);
+      mma_commit(&bar);
+    }
+    if (A.normals && p < 99) {                     // dN2w[j][k] / dN2b[j] on the CUDA cores (needs NH before E1 overwrites it)
+      const int j = p < 96 ? p >> 5 : p - 96, k = p & 31;
+      float s = 0.f;
+      for (int r = 0; r < kTcTile; ++r)
+        s += tile_elem(sm + TS::DNR, r, j, 2) * (p < 96 ? tile_elem(sm + TS::NH, r, k, 4) : 1.f);
+      g_n2 += s;
+    }
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    __syncthreads();                               // all NH reads above are done
+    epi_grad64(lane_addr + TM_D1, sm + TS::A2C, p, false, 0);
+    if (A.normals) {
+      float v[32];
+      tmem_ld16(lane_addr + TM_DN, v);
+      tmem_ld16(lane_addr + TM_DN + 16, v + 16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float a[8];
+        ld_chunk(sm + TS::NH, chunk_off(p, c, 4), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * c + j] = a[j] > 0.f ? v[8 * c + j] : 0.f;
+        st_chunk(sm + TS::NH, chunk_off(p, c, 4), v + 8 * c);
+      }
+    }
+    fence_async_smem(); fence_before_sync(); __syncthreads();
+    // B2: dC1 += dA2pre^T A1c ; dA1 = dA2pre C1
+    if (t0) {
+      fence_after_sync();
+      issue(tmem + TM_GC1, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::A1C, 64), instr_desc(64, 64, 1, 1), 8, !first);
+      issue(tmem + TM_D1, k_major(sm + TS::A2C, 64), mn_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 1), 4, false);
+      mma_commit(&bar);
+    }
+    if (A.normals) {                               // dN0w[j][k] (k < 15) and dN0b[j] (k == 15): 4 outputs per thread
+      const int j = p >> 2, k0 = (p & 3) * 4;
+      for (int r = 0; r < kTcTile; ++r) {
+        const float d = tile_elem(sm + TS::NH, r, j, 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          g_n0[i] += d * ((k0 + i) < 15 ? tile_elem(sm + TS::CIN, r, 16 + k0 + i, 4) : 1.f);
+      }
+    }
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    epi_grad64(lane_addr + TM_D1, sm + TS::A1C, p, false, 0);
+    fence_async_smem(); fence_before_sync(); __syncthreads();
+    // B3: dC0 += dA1pre^T CIN ; dCIN = dA1pre C0 ; (normals) dgeo_n = dNHpre N0
+    if (t0) {
+      fence_after_sync();
+      issue(tmem + TM_GC0, mn_major(sm + TS::A1C, 64), mn_major(sm + TS::CIN, 32), instr_desc(64, 32, 1, 1), 8, !first);
+      issue(tmem + TM_D1, k_major(sm + TS::A1C, 64), mn_major(sm + TS::W_C0, 32), instr_desc(128, 32, 0, 1), 4, false);
+      if (A.normals)
+        issue(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    {
+      float g[17];
+      tmem_ld16(lane_addr + TM_D1 + 16, g + 1);      // dCIN[16..32) = dgeo[0..15) + pad
+      if (dsh) {
+        float v[16];
+        tmem_ld16(lane_addr + TM_D1, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4 *o = reinterpret_cast<float4 *>(dsh + (base + p) * dsh_stride);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+      }
+      tmem_ld_wait();
+      if (A.normals) {
+        float v[16];
+        tmem_ld16(lane_addr + TM_D2, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 15; ++j) g[1 + j] += v[j];
+      }
+      g[0] = d_o[3];                                 // dsigma (keep mask applied above when C == 4)
+      st_chunk(sm + TS::DH2, chunk_off(p, 0, 2), g);
+      st_chunk(sm + TS::DH2, chunk_off(p, 1, 2), g + 8);
+    }
+    fence_async_smem(); fence_before_sync(); __syncthreads();
+    // B4: dS1^T += H1^T dH2 ; dH1 = dH2 S1
+    if (t0) {
+      fence_after_sync();
+      issue(tmem + TM_GS1, mn_major(sm + TS::A1, 64), mn_major(sm + TS::DH2, 16), instr_desc(64, 16, 1, 1), 8, !first);
+      issue(tmem + TM_D1, k_major(sm + TS::DH2, 16), mn_major(sm + TS::W_S1, 64), instr_desc(128, 64, 0, 1), 1, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    epi_grad64(lane_addr + TM_D1, sm + TS::A1, p, true, h1_mask);
+    fence_async_smem(); fence_before_sync(); __syncthreads();
+    // B5: dS0 += dH1pre^T X ; dX = dH1pre S0
+    if (t0) {
+      fence_after_sync();
+      issue(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
+      issue(tmem + TM_D1, k_major(sm + TS::A1, 64), mn_major(sm + TS::W_S0, 32), instr_desc(128, 32, 0, 1), 4, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    {
+      float v[32];
+      tmem_ld16(lane_addr + TM_D1, v);
+      tmem_ld16(lane_addr + TM_D1 + 16, v + 16);
+      tmem_ld_wait();
+      if (valid) {
+        float4 *o = reinterpret_cast<float4 *>(dfeat + (base + p) * dfeat_stride);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+    }
+    first = false;
+    fence_before_sync(); __syncthreads();
+  }
+  // flush the weight gradients (every MMA has completed: the last commit was waited on)
+  fence_after_sync();
+  const bool owner = lane < 16;
+  const int row = warp * 16 + lane;
+  if (!first) {
+    flush_acc(lane_addr + TM_GC1, 64, owner, row, G.c1, 64, 64, 64, false);
+    flush_acc(lane_addr + TM_GS0, 32, owner, row, G.s0, 32, 64, 32, false);
+    flush_acc(lane_addr + TM_GC0, 32, owner, row, G.c0, 31, 64, 31, false);
+    flush_acc(lane_addr + TM_GS1, 16, owner, row, G.s1, 64, 64, 16, true);
+    flush_acc(lane_addr + TM_GC2, 16, owner, row, G.c2, 64, 64, 3, true);
+    if (A.normals) {
+      if (p < 96 && G.n2w) atomicAdd(G.n2w + (p >> 5) * 32 + (p & 31), g_n2);
+      else if (p < 99 && G.n2b) atomicAdd(G.n2b + (p - 96), g_n2);
+      const int j = p >> 2, k0 = (p & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (k0 + i < 15) { if (G.n0w) atomicAdd(G.n0w + j * 15 + k0 + i, g_n0[i]); }
+        else if (G.n0b) atomicAdd(G.n0b + j, g_n0[i]);
+      }
+    }
+  }
+  fence_before_sync(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TM_BWD_COLS);
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int pn_tc_selftest(const int32_t *cfg, const float *A, const float *B, float *D, pn_stream_t stream) {
+  PN_REQUIRE(cfg && A && B && D, PN_EINVAL, "NULL pointer argument");
+  SelfTestArgs a;
+  a.ra = cfg[0]; a.ca = cfg[1]; a.rb = cfg[2]; a.cb = cfg[3]; a.M = cfg[4]; a.N = cfg[5]; a.ksteps = cfg[6];
+  a.a_mn = cfg[7]; a.b_mn = cfg[8];
+  a.lbo_a = cfg[9]; a.sbo_a = cfg[10]; a.adv_a = cfg[11]; a.lbo_b = cfg[12]; a.sbo_b = cfg[13]; a.adv_b = cfg[14];
+  PN_REQUIRE(a.ca % 8 == 0 && a.cb % 8 == 0 && a.ra % 8 == 0 && a.rb % 8 == 0, PN_ESHAPE, "tile dims must be multiples of 8");
+  PN_REQUIRE((a.M == 64 || a.M == 128) && a.N >= 16 && a.N <= 64 && a.N % 16 == 0, PN_ESHAPE, "M in {64,128}, N in 16..64");
+  const size_t smem = ((size_t)(a.ra * a.ca * 2 + 127) / 128) * 128 + (size_t)a.rb * a.cb * 2 + 4096;
+  PN_REQUIRE(smem <= 200 * 1024, PN_ESHAPE, "tiles too large");
+  cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  tc_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(a, A, B, D);
+  count_launch();
+  return check_launch("tc_selftest_kernel");
+}
+
+namespace pn {
+int check_mlp_args(const pn_mlp_weights *w, const pn_mlp_input *in, bool *normals);   // mlp_fp32.cu
+}
+
+extern "C" int pn_mlp_fwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, float *out, pn_stream_t stream) {
+  bool normals = false;
+  if (int e = check_mlp_args(w, in, &normals)) return e;
+  PN_REQUIRE(out != nullptr, PN_EINVAL, "out is NULL");
+  if (in->n_points == 0) return 0;
+  TcArgs A;
+  A.w = *w; A.in = *in; A.normals = normals; A.C = normals ? 7 : 4;
+  PN_REQUIRE(A.C == 7 || ((uintptr_t)out & 15) == 0, PN_EINVAL, "out must be 16-byte aligned");
+  const int smem = TS::FWD_END;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_fwd): %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  const int64_t tiles = ceil_div(in->n_points, kTcTile);
+  const int64_t cap = (int64_t)sm_count() * 3;          // 3 CTAs/SM: 3 x 128 TMEM columns, 3 x 63 KB smem
+  const int blocks = (int)(tiles < cap ? tiles : cap);
+  mlp_tc_fwd_kernel<<<blocks, kTcTile, smem, as_stream(stream)>>>(A, out);
+  count_launch();
+  return check_launch("mlp_tc_fwd_kernel");
+}
+
+extern "C" int pn_mlp_bwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, const float *dout, float *dfeat,
+                               int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads *dw,
+                               pn_stream_t stream) {
+  bool normals = false;
+  if (int e = check_mlp_args(w, in, &normals)) return e;
+  PN_REQUIRE(dout && dfeat && dw, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(dfeat_stride >= 32 && dfeat_stride % 4 == 0 && ((uintptr_t)dfeat & 15) == 0, PN_EINVAL,
+             "dfeat stride/alignment");
+  PN_REQUIRE(dsh == nullptr || (in->sh != nullptr && dsh_stride >= 16 && dsh_stride % 4 == 0 &&
+                                ((uintptr_t)dsh & 15) == 0),
+             PN_EINVAL, "dsh needs in->sh, stride >= 16 (multiple of 4) and 16-byte alignment");
+  if (in->n_points == 0) return 0;
+  TcArgs A;
+  A.w = *w; A.in = *in; A.normals = normals; A.C = normals ? 7 : 4;
+  const int smem = TS::BWD_END;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  const int64_t tiles = ceil_div(in->n_points, kTcTile);
+  const int64_t cap = (int64_t)sm_count() * 2;          // 2 CTAs/SM: 2 x 256 TMEM columns, 2 x 107 KB smem
+  const int blocks = (int)(tiles < cap ? tiles : cap);
+  mlp_tc_bwd_kernel<<<blocks, kTcTile, smem, as_stream(stream)>>>(A, dout, dfeat, dfeat_stride, dsh, dsh_stride, *dw);
+  count_launch();
+  return check_launch("mlp_tc_bwd_kernel");
+}

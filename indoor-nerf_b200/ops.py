@@ -2,6 +2,7 @@
 forward and backward kernels together.  Nothing here computes on the CPU or falls back to torch ops for
 the hot path; torch allocates the outputs and provides the stream."""
 import ctypes
+import os
 
 import torch
 
@@ -9,6 +10,20 @@ from . import _lib
 from ._lib import HashGrid, MlpInput, MlpWeights, call, dptr, fcontig, stream
 
 _MLP_KEYS = ("s0", "s1", "c0", "c1", "c2", "n0w", "n0b", "n2w", "n2b")
+
+# Arithmetic mode of the NeRFSmall kernels: "fp32" (FFMA, 1e-5 parity) or "bf16" (tcgen05 tensor cores, 2e-3).
+_MLP_MODE = os.environ.get("POCKETNERF_MLP", "fp32")
+
+
+def set_mlp_mode(mode):
+    global _MLP_MODE
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("mlp mode must be 'fp32' or 'bf16'")
+    _MLP_MODE = mode
+
+
+def get_mlp_mode():
+    return _MLP_MODE
 
 
 def _guard(t):
@@ -167,18 +182,19 @@ def _mlp_input(feat, sh, dirs, samples_per_ray, act_q, keep):
     return i
 
 
-def mlp_fwd(w, feat, sh=None, dirs=None, samples_per_ray=1, act_q=None, keep=None):
+def mlp_fwd(w, feat, sh=None, dirs=None, samples_per_ray=1, act_q=None, keep=None, mode=None):
     """w: dict of contiguous fp32 CUDA weights (keys s0,s1,c0,c1,c2[,n0w,n0b,n2w,n2b]).  Returns
     out[P, 4|7].   Reference: run_nerf_helpers.py:265-306 (+ run_nerf.py:59-66 when dirs/keep given)."""
     C = 7 if w.get("n0w") is not None else 4
     out = torch.empty((feat.shape[0], C), dtype=torch.float32, device=feat.device)
     with _guard(feat):
         ws, inp = _weights_struct(w), _mlp_input(feat, sh, dirs, samples_per_ray, act_q, keep)
-        call("pn_mlp_fwd", ctypes.byref(ws), ctypes.byref(inp), dptr(out), stream())
+        call("pn_mlp_fwd_bf16" if (mode or _MLP_MODE) == "bf16" else "pn_mlp_fwd", ctypes.byref(ws), ctypes.byref(inp),
+             dptr(out), stream())
     return out
 
 
-def mlp_bwd(w, feat, dout, sh=None, dirs=None, samples_per_ray=1, act_q=None, keep=None, want_dsh=False):
+def mlp_bwd(w, feat, dout, sh=None, dirs=None, samples_per_ray=1, act_q=None, keep=None, want_dsh=False, mode=None):
     """Returns dfeat[P,32], dsh[P,16] or None, dict of weight gradients."""
     dout = fcontig(dout)
     P = feat.shape[0]
@@ -188,7 +204,8 @@ def mlp_bwd(w, feat, dout, sh=None, dirs=None, samples_per_ray=1, act_q=None, ke
     with _guard(feat):
         ws, inp = _weights_struct(w), _mlp_input(feat, sh, dirs, samples_per_ray, act_q, keep)
         gs = _weights_struct(dw)
-        call("pn_mlp_bwd", ctypes.byref(ws), ctypes.byref(inp), dptr(dout), dptr(dfeat), 32,
+        call("pn_mlp_bwd_bf16" if (mode or _MLP_MODE) == "bf16" else "pn_mlp_bwd", ctypes.byref(ws), ctypes.byref(inp),
+             dptr(dout), dptr(dfeat), 32,
              dptr(dsh, allow_none=True), 16, ctypes.byref(gs), stream())
     return dfeat, dsh, dw
 
@@ -201,7 +218,8 @@ class MlpFn(torch.autograd.Function):
         x = fcontig(x)
         w = {k: fcontig(t.detach()) for k, t in zip(keys, weights)}
         feat, sh = x[:, :32], x[:, 32:48]
-        out = mlp_fwd(w, feat, sh=sh, act_q=act_q)
+        ctx.mode = _MLP_MODE
+        out = mlp_fwd(w, feat, sh=sh, act_q=act_q, mode=ctx.mode)
         ctx.keys, ctx.act_q = keys, act_q
         ctx.save_for_backward(x, *weights)
         return out
@@ -210,7 +228,7 @@ class MlpFn(torch.autograd.Function):
     def backward(ctx, dout):
         x, *weights = ctx.saved_tensors
         w = {k: fcontig(t.detach()) for k, t in zip(ctx.keys, weights)}
-        dfeat, dsh, dw = mlp_bwd(w, x[:, :32], dout, sh=x[:, 32:48], act_q=ctx.act_q, want_dsh=True)
+        dfeat, dsh, dw = mlp_bwd(w, x[:, :32], dout, sh=x[:, 32:48], act_q=ctx.act_q, want_dsh=True, mode=ctx.mode)
         dx = torch.cat([dfeat, dsh], -1) if ctx.needs_input_grad[0] else None
         return (dx, None, None) + tuple(dw[k] for k in ctx.keys)
 
@@ -229,7 +247,8 @@ class FieldFn(torch.autograd.Function):
         dirs = fcontig(viewdirs)
         w = {k: fcontig(t.detach()) for k, t in zip(keys, weights)}
         feat, keep = hash_encode_fwd(grid, [t.detach() for t in tables], pts, qparams)
-        out = mlp_fwd(w, feat, dirs=dirs, samples_per_ray=S, act_q=act_q, keep=keep)
+        ctx.mode = _MLP_MODE
+        out = mlp_fwd(w, feat, dirs=dirs, samples_per_ray=S, act_q=act_q, keep=keep, mode=ctx.mode)
         ctx.grid, ctx.S, ctx.act_q, ctx.keys, ctx.n_tables = grid, S, act_q, keys, n_tables
         ctx.save_for_backward(pts, dirs, feat, keep, *params)
         return out
@@ -239,7 +258,7 @@ class FieldFn(torch.autograd.Function):
         pts, dirs, feat, keep, *params = ctx.saved_tensors
         tables, weights = params[:ctx.n_tables], params[ctx.n_tables:]
         w = {k: fcontig(t.detach()) for k, t in zip(ctx.keys, weights)}
-        dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep)
+        dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep, mode=ctx.mode)
         tgrads = [None] * ctx.n_tables
         if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):
             flat = torch.zeros((ctx.n_tables,) + tuple(tables[0].shape), dtype=torch.float32, device=pts.device)
