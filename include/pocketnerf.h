@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 4
+#define PN_ABI_VERSION 5
 #define PN_MAX_LEVELS 16
 
 #define PN_EINVAL (-1)   /* bad argument */
@@ -218,6 +218,25 @@ int pn_make_points(const float *rays_o, int64_t o_stride, const float *rays_d, i
 int pn_coarse_z(const float *near, const float *far, int64_t nf_stride, const float *t_vals,
                 const float *t_rand, int64_t n_rays, int n_samples, int lindisp, float *z,
                 pn_stream_t stream);
+
+/* ---- train-step surroundings ------------------------------------------------------ */
+
+/* total_variation_loss (loss.py:11-43) for all levels in one launch.  cube: host[n_levels] cube sizes;
+ * min_vertex: device int64 [n_levels,3] (the torch.randint draws of loss.py:26); loss: device [n_levels],
+ * caller-zeroed, receives (tv_x+tv_y+tv_z)/cube_size per level. */
+int pn_tv_loss_fwd(const float *const *tables, int n_levels, int log2_hashmap_size, const int32_t *cube,
+                   const int64_t *min_vertex, float *loss, pn_stream_t stream);
+/* dtables[l] += dloss[l] * d loss_l / d table_l  (atomics into caller-owned dense buffers). */
+int pn_tv_loss_bwd(const float *const *tables, float *const *dtables, int n_levels, int log2_hashmap_size,
+                   const int32_t *cube, const int64_t *min_vertex, const float *dloss, pn_stream_t stream);
+
+/* One RAdam update (radam.py:55-88) over n contiguous fp32 elements: moments always; mode 2 = rectified
+ * adaptive step p += -wd*lr*p; p += -step_size*lr * m/(sqrt(v)+eps); mode 1 = p += -step_size*lr*m
+ * (degenerated_to_sgd); mode 0 = moments only (N_sma < 5).  The scalars are computed by the host exactly as
+ * radam.py:63-78 does. */
+int pn_radam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
+                  float beta2, float eps, float weight_decay_times_lr, float step_size_times_lr, int mode,
+                  pn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpocketnerf.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LEVELS = 16
 QROW = 8
 
@@ -51,6 +51,9 @@ _SIGNATURES = {
     "pn_mlp_bwd_bf16": [ctypes.POINTER(MlpWeights), ctypes.POINTER(MlpInput), _P, _P, _L, _P, _L,
                         ctypes.POINTER(MlpWeights), _P],
     "pn_tc_selftest": [_P, _P, _P, _P, _P],
+    "pn_tv_loss_fwd": [_P, _I, _I, _P, _P, _P, _P],
+    "pn_tv_loss_bwd": [_P, _P, _I, _I, _P, _P, _P, _P],
+    "pn_radam_step": [_P, _P, _P, _P, _L] + [ctypes.c_float] * 5 + [_I, _P],
     "pn_composite_fwd": [_P, _I, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "pn_composite_bwd": [_P, _I, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pn_sample_pdf": [_P, _P, _L, _P, _L, _L, _I, _I, _P, _P, _P, _P],

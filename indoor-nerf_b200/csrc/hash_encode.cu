@@ -9,14 +9,12 @@
 // 126 MB L2; the [P,32] output is staged through shared memory so that each warp writes whole
 // 128-byte lines.  HBM traffic per point is then the algorithmic minimum 12 B in + 128 B out.
 #include "hash_core.cuh"
+#include "hash_scatter.cuh"
 
 namespace pn {
 
 struct TablePtrs {
   const float2 *t[PN_MAX_LEVELS];
-};
-struct GradPtrs {
-  float2 *t[PN_MAX_LEVELS];
 };
 
 constexpr int kHashThreads = 128;
@@ -114,21 +112,11 @@ hash_bwd_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ G
     __syncwarp();
     float xv[3] = {0.f, 0.f, 0.f};
     if (valid) load_point(x, p, xv);
-    if (valid) {
 #pragma unroll 2
-      for (int l = 0; l < G.n_levels; ++l) {
-        const float g0 = st[lane * kStagePitch + 2 * l + 0];
-        const float g1 = st[lane * kStagePitch + 2 * l + 1];
-        if (g0 == 0.f && g1 == 0.f) continue;    // e.g. masked / zero-weight samples
-        Cell c;
-        point_cell(G, l, xv, c);
-        float2 *tab = D.t[l];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float2 v = make_float2(corner_weight_times(g0, c.w, k), corner_weight_times(g1, c.w, k));
-          atomicAdd(tab + corner_index(G, c, k), v);
-        }
-      }
+    for (int l = 0; l < G.n_levels; ++l) {
+      const float g0 = valid ? st[lane * kStagePitch + 2 * l + 0] : 0.f;
+      const float g1 = valid ? st[lane * kStagePitch + 2 * l + 1] : 0.f;
+      scatter_level(G, D.t[l], l, xv, g0, g1, lane);
     }
     __syncwarp();
   }

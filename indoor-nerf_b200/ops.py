@@ -137,6 +137,44 @@ class HashEncodeFn(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
+class TVLossFn(torch.autograd.Function):
+    """losses[L] = TVLossFn.apply(min_vertex[L,3] int64, cubes (tuple of ints), log2T, *tables):
+    total_variation_loss (loss.py:11-43) of every level in one launch, and its gradient in one more."""
+
+    @staticmethod
+    def forward(ctx, min_vertex, cubes, log2T, *tables):
+        mv = min_vertex.to(torch.int64).contiguous()
+        dev = tables[0].device
+        L = len(tables)
+        loss = torch.zeros(L, dtype=torch.float32, device=dev)
+        cube = (ctypes.c_int32 * L)(*[int(c) for c in cubes])
+        with _guard(tables[0]):
+            call("pn_tv_loss_fwd", _ptr_array([t.detach() for t in tables]), L, int(log2T), cube,
+                 dptr(mv, torch.int64), dptr(loss), stream())
+        ctx.cubes, ctx.log2T = tuple(int(c) for c in cubes), int(log2T)
+        ctx.save_for_backward(mv, *tables)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        mv, *tables = ctx.saved_tensors
+        L = len(tables)
+        flat = torch.zeros((L,) + tuple(tables[0].shape), dtype=torch.float32, device=tables[0].device)
+        cube = (ctypes.c_int32 * L)(*ctx.cubes)
+        with _guard(flat):
+            call("pn_tv_loss_bwd", _ptr_array([t.detach() for t in tables]), _ptr_array(list(flat.unbind(0))), L,
+                 ctx.log2T, cube, dptr(mv, torch.int64), dptr(fcontig(dloss)), stream())
+        return (None, None, None) + tuple(flat.unbind(0))
+
+
+def radam_step(p, g, m, v, beta1, beta2, eps, wd_lr, step_lr, mode):
+    """One fused RAdam update over contiguous fp32 CUDA buffers of equal numel (radam.py:55-88)."""
+    n = p.numel()
+    with _guard(p):
+        call("pn_radam_step", dptr(p), dptr(g), dptr(m), dptr(v), n, float(beta1), float(beta2), float(eps),
+             float(wd_lr), float(step_lr), int(mode), stream())
+
+
 # ---------------------------------------------------------------------------------------------------
 # view directions
 # ---------------------------------------------------------------------------------------------------

@@ -1,7 +1,11 @@
-"""RAdam with the reference's constructor, update rule and state layout (radam.py:5-94), written with
-torch's multi-tensor (_foreach) ops: one fused launch per elementwise stage over all parameters of a
-group instead of ~12 launches per parameter.  The optimiser stays PyTorch by design (BASELINE.json
-north_star); a flat fused CUDA step is the first item of SURVEY.md §8f."""
+"""RAdam with the reference's constructor, update rule and state layout (radam.py:5-94).
+
+CUDA parameters are updated by ONE fused kernel per contiguous run of parameters (pn_radam_step): the 16
+hash tables are views of one [L,T,2] buffer and their gradients views of one flat buffer, so the whole
+64 MiB table update is a single elementwise pass (7 x 64 MiB of traffic) instead of ~12 framework launches
+per table.  The moments of such a run are allocated as one flat buffer and exposed per parameter, so
+``state_dict()`` keeps the reference's per-parameter layout ('step', 'exp_avg', 'exp_avg_sq').  CPU
+parameters (unit tests) use torch's multi-tensor ops."""
 import math
 
 import torch
@@ -34,6 +38,84 @@ class RAdam(Optimizer):
             step_size = -1
         return n_sma, step_size
 
+    @staticmethod
+    def _runs(ps):
+        """Split a list of parameters into maximal runs that are adjacent in memory (data and grad)."""
+        runs, cur = [], []
+        for p in ps:
+            ok = (cur and p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
+                  and p.grad.dtype == torch.float32
+                  and p.untyped_storage().data_ptr() == cur[-1].untyped_storage().data_ptr()
+                  and p.grad.untyped_storage().data_ptr() == cur[-1].grad.untyped_storage().data_ptr()
+                  and p.data_ptr() == cur[-1].data_ptr() + cur[-1].numel() * 4
+                  and p.grad.data_ptr() == cur[-1].grad.data_ptr() + cur[-1].numel() * 4)
+            if ok:
+                cur.append(p)
+            else:
+                if cur:
+                    runs.append(cur)
+                cur = [p]
+        if cur:
+            runs.append(cur)
+        return runs
+
+    @staticmethod
+    def _param_runs(ps):
+        """Runs of parameters that are adjacent views of one storage (the hash tables)."""
+        runs, cur = [], []
+        for p in ps:
+            ok = (cur and p.is_cuda and p.is_contiguous() and p.dtype == cur[-1].dtype
+                  and p.untyped_storage().data_ptr() == cur[-1].untyped_storage().data_ptr()
+                  and p.data_ptr() == cur[-1].data_ptr() + cur[-1].numel() * p.element_size())
+            if ok:
+                cur.append(p)
+            else:
+                if cur:
+                    runs.append(cur)
+                cur = [p]
+        if cur:
+            runs.append(cur)
+        return runs
+
+    def _init_state(self, ps):
+        """Moments for parameters without state; adjacent parameters share one flat moment buffer."""
+        new = [p for p in ps if len(self.state[p]) == 0]
+        for run in self._param_runs(new):
+            n = sum(p.numel() for p in run)
+            m = torch.zeros(n, dtype=run[0].dtype, device=run[0].device)
+            v = torch.zeros(n, dtype=run[0].dtype, device=run[0].device)
+            off = 0
+            for p in run:
+                st = self.state[p]
+                st["step"] = 0
+                st["exp_avg"] = m[off:off + p.numel()].view_as(p)
+                st["exp_avg_sq"] = v[off:off + p.numel()].view_as(p)
+                off += p.numel()
+
+    def _fused_cuda(self, ps, group, step, n_sma, step_size):
+        from . import ops
+        beta1, beta2 = group["betas"]
+        mode = 2 if n_sma >= 5 else (1 if step_size > 0 else 0)
+        lr, wd = group["lr"], group["weight_decay"]
+        for run in self._runs(ps):
+            first = run[0]
+            n = sum(p.numel() for p in run)
+            m0, v0 = self.state[first]["exp_avg"], self.state[first]["exp_avg_sq"]
+            flat_state = all(self.state[p]["exp_avg"].data_ptr() == m0.data_ptr() + (p.data_ptr() - first.data_ptr())
+                             and self.state[p]["exp_avg_sq"].data_ptr() == v0.data_ptr() + (p.data_ptr() - first.data_ptr())
+                             and self.state[p]["exp_avg"].untyped_storage().data_ptr() == m0.untyped_storage().data_ptr()
+                             and self.state[p]["exp_avg_sq"].untyped_storage().data_ptr() == v0.untyped_storage().data_ptr()
+                             for p in run)
+            if len(run) > 1 and flat_state:
+                as1d = lambda t: torch.as_strided(t, (n,), (1,))
+                ops.radam_step(as1d(first.data), as1d(first.grad), as1d(m0), as1d(v0), beta1, beta2, group["eps"],
+                               wd * lr, step_size * lr, mode)
+            else:
+                for p in run:
+                    st = self.state[p]
+                    ops.radam_step(p.data.view(-1), p.grad.view(-1), st["exp_avg"].view(-1), st["exp_avg_sq"].view(-1),
+                                   beta1, beta2, group["eps"], wd * lr, step_size * lr, mode)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -43,19 +125,21 @@ class RAdam(Optimizer):
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             by_step = {}
-            for p in group["params"]:
-                if p.grad is None:
-                    continue
+            live = [p for p in group["params"] if p.grad is not None]
+            for p in live:
                 if p.grad.is_sparse:
                     raise RuntimeError("RAdam does not support sparse gradients")
+            self._init_state(live)
+            for p in live:
                 st = self.state[p]
-                if len(st) == 0:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
                 by_step.setdefault(st["step"], []).append(p)
             for step, ps in by_step.items():
+                if all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
+                       and p.grad.dtype == torch.float32 for p in ps):
+                    n_sma, step_size = self._rectification(step, beta1, beta2, self.degenerated_to_sgd)
+                    self._fused_cuda(ps, group, step, n_sma, step_size)
+                    continue
                 grads = [p.grad for p in ps]
                 m = [self.state[p]["exp_avg"] for p in ps]
                 v = [self.state[p]["exp_avg_sq"] for p in ps]

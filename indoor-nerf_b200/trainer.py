@@ -5,7 +5,7 @@ stay in the reference's own torch code."""
 import torch
 
 from . import parallel
-from .loss import total_variation_loss
+from .loss import total_variation_loss_all
 from .render import render
 from .run_nerf_helpers import img2mse, mse2psnr
 
@@ -31,10 +31,7 @@ class Trainer:
             loss = loss + img2mse(extras["rgb0"], target_s) / w
         sparsity = self.args.sparse_loss_weight * (extras["sparsity_loss"].sum() + extras["sparsity_loss0"].sum())
         loss = loss + sparsity
-        e = self.embed_fn
-        tv = sum(total_variation_loss(e.embeddings[i], e.base_resolution, e.finest_resolution, i, e.log2_hashmap_size,
-                                      n_levels=e.n_levels) for i in range(e.n_levels))
-        loss = loss + self.tv_weight * tv / w
+        loss = loss + self.tv_weight * total_variation_loss_all(self.embed_fn) / w
         return loss, img_loss
 
     def step(self, batch_rays, target_s, chunk=None):
