@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 5
+#define PN_ABI_VERSION 6
 #define PN_MAX_LEVELS 16
 
 #define PN_EINVAL (-1)   /* bad argument */
@@ -152,6 +152,24 @@ int pn_mlp_fwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, float *out,
 int pn_mlp_bwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, const float *dout, float *dfeat,
                     int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads *dw,
                     pn_stream_t stream);
+
+/* run_network (run_nerf.py:53-68) as ONE kernel in the bf16 tensor-core mode: hash-grid encode (16 levels) ->
+ * SH of the ray's view direction -> NeRFSmall -> keep mask, for pts[n_points,3] with point p belonging to ray
+ * p / samples_per_ray.  The [P,32] feature tensor never reaches HBM in fp32: the kernel computes each tile's
+ * features straight into the MMA operand tile in shared memory and (when feat_tiles != NULL) saves that tile —
+ * bf16, 8 KB per 128 points, already in operand layout — for the backward.
+ *   out [n_points, 4|7], keep [n_points] (may be NULL), feat_tiles ceil(n_points/128)*8192 bytes (may be NULL). */
+int pn_field_fwd_bf16(const pn_hash_grid *grid, const float *const *tables, const float *qparams,
+                      const pn_mlp_weights *w, const float *pts, const float *dirs, int samples_per_ray,
+                      const float *act_q, int64_t n_points, float *out, uint8_t *keep, void *feat_tiles,
+                      pn_stream_t stream);
+/* Backward of pn_field_fwd_bf16 as ONE kernel: NeRFSmall backward on the saved feature tiles and, from its
+ * epilogue, the run-aggregated scatter-add of the feature gradient into dtables (caller-zeroed, accumulated);
+ * weight gradients accumulated into dw.  The [P,32] feature gradient never reaches HBM. */
+int pn_field_bwd_bf16(const pn_hash_grid *grid, float *const *dtables, const pn_mlp_weights *w,
+                      const void *feat_tiles, const float *pts, const float *dirs, int samples_per_ray,
+                      const float *act_q, const uint8_t *keep, const float *dout, int64_t n_points,
+                      const pn_mlp_grads *dw, pn_stream_t stream);
 
 /* Diagnostic: one tcgen05 GEMM with caller-chosen shared-memory descriptor fields (cfg[15], see
  * mlp_tc.cu) — proves the K-major / MN-major operand readings and the TMEM accumulator layouts on the

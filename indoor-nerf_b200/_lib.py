@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpocketnerf.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LEVELS = 16
 QROW = 8
 
@@ -50,6 +50,9 @@ _SIGNATURES = {
     "pn_mlp_fwd_bf16": [ctypes.POINTER(MlpWeights), ctypes.POINTER(MlpInput), _P, _P],
     "pn_mlp_bwd_bf16": [ctypes.POINTER(MlpWeights), ctypes.POINTER(MlpInput), _P, _P, _L, _P, _L,
                         ctypes.POINTER(MlpWeights), _P],
+    "pn_field_fwd_bf16": [ctypes.POINTER(HashGrid), _P, _P, ctypes.POINTER(MlpWeights), _P, _P, _I, _P, _L, _P, _P, _P, _P],
+    "pn_field_bwd_bf16": [ctypes.POINTER(HashGrid), _P, ctypes.POINTER(MlpWeights), _P, _P, _P, _I, _P, _P, _P, _L,
+                          ctypes.POINTER(MlpWeights), _P],
     "pn_tc_selftest": [_P, _P, _P, _P, _P],
     "pn_tv_loss_fwd": [_P, _I, _I, _P, _P, _P, _P],
     "pn_tv_loss_bwd": [_P, _P, _I, _I, _P, _P, _P, _P],

@@ -19,6 +19,7 @@ struct HashGridDev {
   float bmin[3];
   float bmax[3];
   float g[PN_MAX_LEVELS][3];   // (bmax - bmin) / res[l], IEEE fp32, computed once on the host
+  float rg[PN_MAX_LEVELS][3];  // 1 / g (bf16 paths only)
   int n_levels;
   uint32_t mask;
 };
@@ -29,11 +30,18 @@ inline HashGridDev make_grid_dev(const pn_hash_grid &h) {
   for (int a = 0; a < 3; ++a) { G.bmin[a] = h.box_min[a]; G.bmax[a] = h.box_max[a]; }
   for (int l = 0; l < PN_MAX_LEVELS; ++l)
     for (int a = 0; a < 3; ++a)
+    {
       G.g[l][a] = (l < h.n_levels) ? pn_div(pn_sub(h.box_max[a], h.box_min[a]), h.resolution[l]) : 1.0f;
+      G.rg[l][a] = 1.0f / G.g[l][a];
+    }
   G.n_levels = h.n_levels;
   G.mask = (1u << h.log2_hashmap_size) - 1u;
   return G;
 }
+
+struct TablePtrs {
+  const float2 *t[PN_MAX_LEVELS];
+};
 
 #define PN_PRIME_Y 2654435761u
 #define PN_PRIME_Z 805459861u
@@ -56,6 +64,10 @@ PN_HD bool point_keep(const HashGridDev &G, const float x[3]) {
   return k;
 }
 
+// EXACT_W = true reproduces the reference's interpolation weights bit for bit (IEEE division, no contraction);
+// EXACT_W = false is for the bf16 paths, where the features are rounded to 8 bits of mantissa anyway: the voxel
+// index is still the exact one, the weight is (x - vmin) * (1/g) with ordinary contraction (error ~1e-6).
+template <bool EXACT_W = true>
 PN_HD void point_cell(const HashGridDev &G, int level, const float x[3], Cell &c) {
   uint32_t ii[3];
 #pragma unroll
@@ -65,9 +77,13 @@ PN_HD void point_cell(const HashGridDev &G, int level, const float x[3], Cell &c
     const float xc = fminf(fmaxf(x[a], G.bmin[a]), G.bmax[a]);
     const float fi = floorf(pn_div(pn_sub(xc, G.bmin[a]), g));
     const int i = (int)fi;                                   // .int() : fi is integral, >= 0
-    const float vmin = pn_add(pn_mul((float)i, g), G.bmin[a]);
-    const float vmax = pn_add(vmin, g);                      // 1.0*g == g exactly
-    c.w[a] = pn_div(pn_sub(x[a], vmin), pn_sub(vmax, vmin));
+    if (EXACT_W) {
+      const float vmin = pn_add(pn_mul((float)i, g), G.bmin[a]);
+      const float vmax = pn_add(vmin, g);                    // 1.0*g == g exactly
+      c.w[a] = pn_div(pn_sub(x[a], vmin), pn_sub(vmax, vmin));
+    } else {
+      c.w[a] = (x[a] - ((float)i * g + G.bmin[a])) * G.rg[level][a];
+    }
     ii[a] = (uint32_t)i;
   }
   c.hx0 = ii[0];
@@ -92,6 +108,14 @@ PN_HD float fake_quant(float x, float scale, float denom, float zp, float qmin, 
   q = fminf(fmaxf(q, qmin), qmax);
   const float dq = pn_mul(pn_sub(q, zp), scale);
   return train_form ? pn_add(x, pn_sub(dq, x)) : dq;
+}
+
+// contraction-friendly trilinear interpolation for the bf16 paths
+PN_HD float trilerp_fast(const float e[8], const float w[3]) {
+  const float c00 = e[0] + w[0] * (e[4] - e[0]), c01 = e[1] + w[0] * (e[5] - e[1]);
+  const float c10 = e[2] + w[0] * (e[6] - e[2]), c11 = e[3] + w[0] * (e[7] - e[3]);
+  const float c0 = c00 + w[1] * (c10 - c00), c1 = c01 + w[1] * (c11 - c01);
+  return c0 + w[2] * (c1 - c0);
 }
 
 // hash_encoding.py:68-78 for one feature channel; e[corner].

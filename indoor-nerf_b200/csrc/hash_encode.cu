@@ -13,9 +13,6 @@
 
 namespace pn {
 
-struct TablePtrs {
-  const float2 *t[PN_MAX_LEVELS];
-};
 
 constexpr int kHashThreads = 128;
 constexpr int kHashWarps = kHashThreads / 32;
@@ -195,7 +192,7 @@ hash_minmax_kernel(const __grid_constant__ HashGridDev G, const __grid_constant_
   }
 }
 
-static int check_grid(const pn_hash_grid *g) {
+int check_grid_args(const pn_hash_grid *g) {
   PN_REQUIRE(g != nullptr, PN_EINVAL, "grid is NULL");
   PN_REQUIRE(g->n_levels >= 1 && g->n_levels <= PN_MAX_LEVELS, PN_ESHAPE, "n_levels %d outside 1..%d",
              g->n_levels, PN_MAX_LEVELS);
@@ -220,7 +217,7 @@ using namespace pn;
 extern "C" int pn_hash_encode_fwd(const pn_hash_grid *grid, const float *const *tables, const float *qparams,
                                   const float *x, int64_t n_points, float *feat, uint8_t *keep,
                                   pn_stream_t stream) {
-  if (int e = check_grid(grid)) return e;
+  if (int e = check_grid_args(grid)) return e;
   PN_REQUIRE(tables && x && feat, PN_EINVAL, "NULL pointer argument");
   PN_REQUIRE(n_points >= 0, PN_EINVAL, "n_points < 0");
   if (n_points == 0) return 0;
@@ -240,7 +237,7 @@ extern "C" int pn_hash_encode_fwd(const pn_hash_grid *grid, const float *const *
 
 extern "C" int pn_hash_encode_bwd(const pn_hash_grid *grid, float *const *dtables, const float *x,
                                   const float *dfeat, int64_t n_points, pn_stream_t stream) {
-  if (int e = check_grid(grid)) return e;
+  if (int e = check_grid_args(grid)) return e;
   PN_REQUIRE(dtables && x && dfeat, PN_EINVAL, "NULL pointer argument");
   PN_REQUIRE(n_points >= 0, PN_EINVAL, "n_points < 0");
   if (n_points == 0) return 0;
@@ -256,7 +253,7 @@ extern "C" int pn_hash_encode_bwd(const pn_hash_grid *grid, float *const *dtable
 
 extern "C" int pn_hash_indices(const pn_hash_grid *grid, const float *x, int64_t n_points, int32_t *idx,
                                pn_stream_t stream) {
-  if (int e = check_grid(grid)) return e;
+  if (int e = check_grid_args(grid)) return e;
   PN_REQUIRE(x && idx, PN_EINVAL, "NULL pointer argument");
   if (n_points <= 0) return 0;
   const HashGridDev G = make_grid_dev(*grid);
@@ -280,7 +277,7 @@ extern "C" int pn_hash_coords(const int64_t *coords, int64_t n, int dim, int log
 
 extern "C" int pn_hash_gather_minmax(const pn_hash_grid *grid, const float *const *tables, const float *x,
                                      int64_t n_points, float *minmax, pn_stream_t stream) {
-  if (int e = check_grid(grid)) return e;
+  if (int e = check_grid_args(grid)) return e;
   PN_REQUIRE(tables && x && minmax, PN_EINVAL, "NULL pointer argument");
   if (n_points <= 0) return 0;
   const HashGridDev G = make_grid_dev(*grid);

@@ -15,10 +15,11 @@ struct GradPtrs {
 };
 
 // All 32 lanes must call this (lanes without a point pass g0 = g1 = 0 and any x).
+template <bool EXACT_W = true>
 __device__ __forceinline__ void scatter_level(const HashGridDev &G, float2 *__restrict__ tab, int level,
                                               const float xv[3], float g0, float g1, int lane) {
   Cell c;
-  point_cell(G, level, xv, c);
+  point_cell<EXACT_W>(G, level, xv, c);
   // run heads: first lane, or voxel differs from the previous lane's
   const uint32_t px = __shfl_up_sync(0xffffffffu, c.hx0, 1), py = __shfl_up_sync(0xffffffffu, c.hy0, 1),
                  pz = __shfl_up_sync(0xffffffffu, c.hz0, 1);

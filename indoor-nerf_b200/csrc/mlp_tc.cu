@@ -4,6 +4,7 @@
 //   memory in the tile layout of tc_common.cuh; the epilogue of each layer (tcgen05.ld -> ReLU -> bf16 ->
 //   st.shared) produces the next layer's A operand.  Nothing but the tile's inputs and outputs touches HBM.
 #include "hash_core.cuh"
+#include "hash_scatter.cuh"
 #include "tc_common.cuh"
 
 namespace pn {
@@ -120,6 +121,20 @@ struct TcArgs {
   int C;
 };
 
+// Extra arguments of the fused field kernels (hash grid + SH + NeRFSmall in one launch).
+struct FieldArgs {
+  HashGridDev G;
+  TablePtrs T;          // forward: tables
+  GradPtrs D;           // backward: table gradients
+  const float *pts;     // [P,3]
+  const float *qparams; // per-level fake-quant rows or NULL
+  uint8_t *keep_out;    // forward: [P]
+  uint4 *featb;         // bf16 feature tiles, 8 KB per 128-point tile, tile layout (forward writes, backward reads)
+};
+
+// input source of a tile's hash features
+enum { SRC_F32 = 0, SRC_HASH = 1, SRC_TILE = 2 };
+
 // fp32 [N x K] row-major global weight (ld = Kvalid) -> bf16 tile [NT x KT], zero padded
 __device__ void load_w_tile(uint8_t *tile, const float *__restrict__ W, int NT, int KT, int Nvalid, int Kvalid) {
   const int C8 = KT / 8;
@@ -167,70 +182,134 @@ __device__ __forceinline__ void issue(uint32_t d, const Opnd &a, const Opnd &b, 
             (accumulate || k > 0) ? 1u : 0u);
 }
 
-// tile inputs: features -> A0, SH -> CIN[0..16)
-__device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, int64_t base, int p, bool valid) {
-  float v[8];
+// Thread mapping: 256 threads per 128-point tile.  Thread (p = tid & 127, half = tid >> 7) owns row p and
+// half of the columns of every epilogue; warps w and w+4 share TMEM lane quarter w (a warp may only touch
+// lanes 32*(warp%4) .. +31), so both halves read the same accumulator rows, different columns.
+constexpr int kTcThreads = 256;
+
+// tile inputs: features -> A0 (16 columns = 8 levels per thread), SH -> CIN[0..16) (half 0).
+//   SRC_F32 : fp32 rows from global (pn_mlp_*_bf16)
+//   SRC_HASH: evaluated here from the point coordinates — 8 levels x 8 gathers per thread — and, when
+//             F.featb is set, also saved as bf16 tiles for the backward (pn_field_fwd_bf16)
+//   SRC_TILE: bf16 tile saved by the forward, copied as is (pn_field_bwd_bf16)
+template <int SRC>
+__device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, const FieldArgs *F, int64_t tile,
+                                               int64_t base, int p, int half, bool valid) {
+  if (SRC == SRC_F32) {
+    float v[8];
 #pragma unroll
-  for (int c8 = 0; c8 < 4; ++c8) {
-    if (valid) {
-      const float4 *src = reinterpret_cast<const float4 *>(A.in.feat + (base + p) * A.in.feat_stride + c8 * 8);
-      const float4 a = __ldg(src), b = __ldg(src + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+    for (int c = 0; c < 2; ++c) {
+      const int c8 = half * 2 + c;
+      if (valid) {
+        const float4 *src = reinterpret_cast<const float4 *>(A.in.feat + (base + p) * A.in.feat_stride + c8 * 8);
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    }
-    st_chunk(sm + TS::A0, chunk_off(p, c8, 4), v);
-  }
-  float o[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) o[j] = 0.f;
-  if (valid) {
-    if (A.in.sh) {
-      const float4 *src = reinterpret_cast<const float4 *>(A.in.sh + (base + p) * A.in.sh_stride);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 a = __ldg(src + q);
-        o[4 * q] = a.x; o[4 * q + 1] = a.y; o[4 * q + 2] = a.z; o[4 * q + 3] = a.w;
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
       }
-    } else {
-      const int64_t r = (base + p) / A.in.samples_per_ray;
-      sh4(__ldg(A.in.dirs + 3 * r), __ldg(A.in.dirs + 3 * r + 1), __ldg(A.in.dirs + 3 * r + 2), o);
+      st_chunk(sm + TS::A0, chunk_off(p, c8, 4), v);
     }
+  } else if (SRC == SRC_TILE) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t off = chunk_off(p, half * 2 + c, 4);
+      *reinterpret_cast<uint4 *>(sm + TS::A0 + off) = __ldg(F->featb + tile * 512 + (off >> 4));
+    }
+  } else {
+    float xv[3] = {0.f, 0.f, 0.f};
+    if (valid) { xv[0] = __ldg(F->pts + 3 * (base + p)); xv[1] = __ldg(F->pts + 3 * (base + p) + 1); xv[2] = __ldg(F->pts + 3 * (base + p) + 2); }
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = half * 8 + i;
+      if (l < F->G.n_levels) {
+        Cell c;
+        point_cell<false>(F->G, l, xv, c);
+        const float2 *__restrict__ tab = F->T.t[l];
+        float e0[8], e1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float2 e = __ldg(tab + corner_index(F->G, c, k)); e0[k] = e.x; e1[k] = e.y; }
+        if (F->qparams) {
+          const float *q = F->qparams + l * PN_QROW;
+          if (q[5] != 0.f) {
+            const float scale = q[0], denom = q[1], zp = q[2], qmin = q[3], qmax = q[4];
+            const bool train_form = q[6] != 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              e0[k] = fake_quant(e0[k], scale, denom, zp, qmin, qmax, train_form);
+              e1[k] = fake_quant(e1[k], scale, denom, zp, qmin, qmax, train_form);
+            }
+          }
+        }
+        f[2 * i] = trilerp_fast(e0, c.w);
+        f[2 * i + 1] = trilerp_fast(e1, c.w);
+      } else {
+        f[2 * i] = 0.f; f[2 * i + 1] = 0.f;
+      }
+    }
+    if (!valid) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint32_t off = chunk_off(p, half * 2 + c, 4);
+      st_chunk(sm + TS::A0, off, f + 8 * c);
+      if (F->featb) F->featb[tile * 512 + (off >> 4)] = *reinterpret_cast<const uint4 *>(sm + TS::A0 + off);
+    }
+    if (half == 0 && valid && F->keep_out) F->keep_out[base + p] = point_keep(F->G, xv) ? 1 : 0;
   }
-  st_chunk(sm + TS::CIN, chunk_off(p, 0, 4), o);
-  st_chunk(sm + TS::CIN, chunk_off(p, 1, 4), o + 8);
+  if (half == 0) {
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = 0.f;
+    if (valid) {
+      if (A.in.sh) {
+        const float4 *src = reinterpret_cast<const float4 *>(A.in.sh + (base + p) * A.in.sh_stride);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 a = __ldg(src + q);
+          o[4 * q] = a.x; o[4 * q + 1] = a.y; o[4 * q + 2] = a.z; o[4 * q + 3] = a.w;
+        }
+      } else {
+        const int64_t r = (base + p) / A.in.samples_per_ray;
+        sh4(__ldg(A.in.dirs + 3 * r), __ldg(A.in.dirs + 3 * r + 1), __ldg(A.in.dirs + 3 * r + 2), o);
+      }
+    }
+    st_chunk(sm + TS::CIN, chunk_off(p, 0, 4), o);
+    st_chunk(sm + TS::CIN, chunk_off(p, 1, 4), o + 8);
+  }
 }
 
-// epilogue of a 64-wide hidden layer: TMEM -> ReLU -> (fake-quant) -> bf16 tile row; returns the ReLU mask
-__device__ __forceinline__ uint64_t epi_hidden64(uint32_t taddr, uint8_t *tile, int p, const float *qrow) {
-  uint64_t mask = 0;
+// epilogue of a 64-wide hidden layer, this thread's 32 columns: TMEM -> ReLU -> (fake-quant) -> bf16 tile row;
+// returns the ReLU mask of those columns
+__device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, int p, int half, const float *qrow) {
+  uint32_t mask = 0;
+  float v[32];
+  tmem_ld16(taddr + half * 32, v);
+  tmem_ld16(taddr + half * 32 + 16, v + 16);
+  tmem_ld_wait();
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    float v[32];
-    tmem_ld16(taddr + h * 32, v);
-    tmem_ld16(taddr + h * 32 + 16, v + 16);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const bool pos = v[j] > 0.f;
-      if (pos) mask |= (1ull << (h * 32 + j));
-      v[j] = pos ? v[j] : 0.f;
-      if (qrow) v[j] = fake_quant(v[j], qrow[0], qrow[1], qrow[2], qrow[3], qrow[4], qrow[6] != 0.f);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) st_chunk(tile, chunk_off(p, h * 4 + c, 8), v + 8 * c);
+  for (int j = 0; j < 32; ++j) {
+    const bool pos = v[j] > 0.f;
+    if (pos) mask |= (1u << j);
+    v[j] = pos ? v[j] : 0.f;
+    if (qrow) v[j] = fake_quant(v[j], qrow[0], qrow[1], qrow[2], qrow[3], qrow[4], qrow[6] != 0.f);
   }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) st_chunk(tile, chunk_off(p, half * 4 + c, 8), v + 8 * c);
   return mask;
 }
+
+#define PN_ROUND_SYNC() do { fence_async_smem(); fence_before_sync(); __syncthreads(); } while (0)
 
 // forward rounds shared by the forward kernel and the backward's recompute.
 // BWD = false: every 64-wide activation goes to A1.   BWD = true: H1 -> A1, colour hidden 1 -> A1C, 2 -> A2C.
 template <bool BWD>
-__device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_t tmem, uint64_t *bar, uint32_t &ph,
-                                           int p, int warp, const float *qrow, float &sigma, float nraw[3],
-                                           uint64_t &h1_mask) {
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+__device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_t tmem, uint32_t lane_addr, uint64_t *bar,
+                                           uint32_t &ph, int p, int half, const float *qrow, float &sigma,
+                                           float nraw[3], uint32_t &h1_mask) {
   const bool t0 = threadIdx.x == 0;
   uint8_t *a1c = BWD ? sm + TS::A1C : sm + TS::A1;
   uint8_t *a2c = BWD ? sm + TS::A2C : sm + TS::A1;
@@ -241,8 +320,8 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     mma_commit(bar);
   }
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
-  h1_mask = epi_hidden64(lane_addr + TM_D1, sm + TS::A1, p, qrow);
-  fence_async_smem(); fence_before_sync(); __syncthreads();
+  h1_mask = epi_hidden32(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
+  PN_ROUND_SYNC();
   // R2: [sigma, geo] = H1 S1^T
   if (t0) {
     fence_after_sync();
@@ -250,7 +329,7 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     mma_commit(bar);
   }
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
-  {
+  if (half == 0) {
     float v[17];
     tmem_ld16(lane_addr + TM_D2, v);
     tmem_ld_wait();
@@ -259,7 +338,7 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     st_chunk(sm + TS::CIN, chunk_off(p, 2, 4), v + 1);      // geo 0..7
     st_chunk(sm + TS::CIN, chunk_off(p, 3, 4), v + 9);      // geo 8..14, 0
   }
-  fence_async_smem(); fence_before_sync(); __syncthreads();
+  PN_ROUND_SYNC();
   // R3: A1c = relu(CIN C0^T);  NH = relu(geo N0^T + b)
   if (t0) {
     fence_after_sync();
@@ -269,19 +348,18 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     mma_commit(bar);
   }
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
-  epi_hidden64(lane_addr + TM_D1, a1c, p, nullptr);
+  epi_hidden32(lane_addr + TM_D1, a1c, p, half, nullptr);
   if (A.normals) {
-    const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS);
-    float v[32];
-    tmem_ld16(lane_addr + TM_DN, v);
-    tmem_ld16(lane_addr + TM_DN + 16, v + 16);
+    const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + half * 16;
+    float v[16];
+    tmem_ld16(lane_addr + TM_DN + half * 16, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + bias[j], 0.f);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) st_chunk(sm + TS::NH, chunk_off(p, c, 4), v + 8 * c);
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + bias[j], 0.f);
+    st_chunk(sm + TS::NH, chunk_off(p, half * 2, 4), v);
+    st_chunk(sm + TS::NH, chunk_off(p, half * 2 + 1, 4), v + 8);
   }
-  fence_async_smem(); fence_before_sync(); __syncthreads();
+  PN_ROUND_SYNC();
   // R4: A2c = relu(A1c C1^T);  raw normal = NH N2^T + b
   if (t0) {
     fence_after_sync();
@@ -291,28 +369,30 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     mma_commit(bar);
   }
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
-  if (A.normals) {
+  if (A.normals && half == 0) {
     const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + 32;
     float v[16];
     tmem_ld16(lane_addr + TM_D2, v);
     tmem_ld_wait();
     nraw[0] = v[0] + bias[0]; nraw[1] = v[1] + bias[1]; nraw[2] = v[2] + bias[2];
   }
-  epi_hidden64(lane_addr + TM_D1, a2c, p, nullptr);
-  fence_async_smem(); fence_before_sync(); __syncthreads();
+  epi_hidden32(lane_addr + TM_D1, a2c, p, half, nullptr);
+  PN_ROUND_SYNC();
 }
 
-__global__ void __launch_bounds__(kTcTile) mlp_tc_fwd_kernel(const TcArgs A, float *__restrict__ out) {
+template <int MIN_CTAS, int SRC>
+__global__ void __launch_bounds__(kTcThreads, MIN_CTAS)
+mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__restrict__ out) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bar;
-  const int p = threadIdx.x, warp = p >> 5;
+  const int tid = threadIdx.x, p = tid & 127, half = tid >> 7, warp = tid >> 5;
   load_all_weights(sm, A);
   if (warp == 0) tmem_alloc(&tmem_slot, TM_FWD_COLS);
-  if (p == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t ph = 0;
   float q[8];
   const float *qrow = nullptr;
@@ -325,30 +405,36 @@ __global__ void __launch_bounds__(kTcTile) mlp_tc_fwd_kernel(const TcArgs A, flo
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kTcTile;
     const bool valid = base + p < A.in.n_points;
-    tc_load_inputs(sm, A, base, p, valid);
-    fence_async_smem(); fence_before_sync(); __syncthreads();
-    float sigma, nraw[3] = {0.f, 0.f, 0.f};
-    uint64_t m;
-    tc_forward<false>(sm, A, tmem, &bar, ph, p, warp, qrow, sigma, nraw, m);
+    tc_load_inputs<SRC>(sm, A, &F, tile, base, p, half, valid);
+    PN_ROUND_SYNC();
+    float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
+    uint32_t m;
+    tc_forward<false>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, m);
     // R5: rgb = A2c C2^T
-    if (p == 0) {
+    if (tid == 0) {
       fence_after_sync();
       issue(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_C2, 64), instr_desc(128, 16, 0, 0), 4, false);
       mma_commit(&bar);
     }
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    float v[16];
-    tmem_ld16(lane_addr + TM_D2, v);
-    tmem_ld_wait();
-    if (valid) {
-      const bool kept = A.in.keep ? (A.in.keep[base + p] != 0) : true;
-      float *o = out + (base + p) * A.C;
-      if (A.C == 4) {
-        *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], kept ? sigma : 0.f);
-      } else {
-        const float nn = fmaxf(sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]), 1e-12f);
-        o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = sigma;
-        o[4] = nraw[0] / nn; o[5] = nraw[1] / nn; o[6] = kept ? nraw[2] / nn : 0.f;
+    if (half == 0) {
+      float v[16];
+      tmem_ld16(lane_addr + TM_D2, v);
+      tmem_ld_wait();
+      if (valid) {
+        bool kept = A.in.keep ? (A.in.keep[base + p] != 0) : true;
+        if (SRC == SRC_HASH) {
+          const float xv[3] = {__ldg(F.pts + 3 * (base + p)), __ldg(F.pts + 3 * (base + p) + 1), __ldg(F.pts + 3 * (base + p) + 2)};
+          kept = point_keep(F.G, xv);
+        }
+        float *o = out + (base + p) * A.C;
+        if (A.C == 4) {
+          *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], kept ? sigma : 0.f);
+        } else {
+          const float nn = fmaxf(sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]), 1e-12f);
+          o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = sigma;
+          o[4] = nraw[0] / nn; o[5] = nraw[1] / nn; o[6] = kept ? nraw[2] / nn : 0.f;
+        }
       }
     }
     fence_before_sync(); __syncthreads();
@@ -356,29 +442,26 @@ __global__ void __launch_bounds__(kTcTile) mlp_tc_fwd_kernel(const TcArgs A, flo
   if (warp == 0) tmem_dealloc(tmem, TM_FWD_COLS);
 }
 
-
-// masked in-place epilogue of an input-gradient GEMM: tile row <- D * [tile row > 0] (or an explicit mask)
-__device__ __forceinline__ void epi_grad64(uint32_t taddr, uint8_t *tile, int p, bool use_mask, uint64_t mask) {
+// masked in-place epilogue of an input-gradient GEMM, this thread's 32 columns:
+// tile row <- D * [tile row > 0] (or an explicit mask)
+__device__ __forceinline__ void epi_grad32(uint32_t taddr, uint8_t *tile, int p, int half, bool use_mask, uint32_t mask) {
+  float v[32];
+  tmem_ld16(taddr + half * 32, v);
+  tmem_ld16(taddr + half * 32 + 16, v + 16);
+  tmem_ld_wait();
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    float v[32];
-    tmem_ld16(taddr + h * 32, v);
-    tmem_ld16(taddr + h * 32 + 16, v + 16);
-    tmem_ld_wait();
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t off = chunk_off(p, half * 4 + c, 8);
+    if (use_mask) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t off = chunk_off(p, h * 4 + c, 8);
-      if (use_mask) {
+      for (int j = 0; j < 8; ++j) v[8 * c + j] = ((mask >> (c * 8 + j)) & 1u) ? v[8 * c + j] : 0.f;
+    } else {
+      float a[8];
+      ld_chunk(tile, off, a);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * c + j] = ((mask >> (h * 32 + c * 8 + j)) & 1ull) ? v[8 * c + j] : 0.f;
-      } else {
-        float a[8];
-        ld_chunk(tile, off, a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * c + j] = a[j] > 0.f ? v[8 * c + j] : 0.f;
-      }
-      st_chunk(tile, off, v + 8 * c);
+      for (int j = 0; j < 8; ++j) v[8 * c + j] = a[j] > 0.f ? v[8 * c + j] : 0.f;
     }
+    st_chunk(tile, off, v + 8 * c);
   }
 }
 
@@ -404,19 +487,21 @@ __device__ __forceinline__ void flush_acc(uint32_t taddr, int ncols, bool owner,
   }
 }
 
-__global__ void __launch_bounds__(kTcTile)
-mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restrict__ dfeat, int64_t dfeat_stride,
-                  float *__restrict__ dsh, int64_t dsh_stride, const pn_mlp_grads G) {
+template <int SRC>
+__global__ void __launch_bounds__(kTcThreads, 2)
+mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout,
+                  float *__restrict__ dfeat, int64_t dfeat_stride, float *__restrict__ dsh, int64_t dsh_stride,
+                  const pn_mlp_grads G) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t bar;
-  const int p = threadIdx.x, warp = p >> 5, lane = p & 31;
+  const int tid = threadIdx.x, p = tid & 127, half = tid >> 7, warp = tid >> 5, lane = tid & 31;
   load_all_weights(sm, A);
   if (warp == 0) tmem_alloc(&tmem_slot, TM_BWD_COLS);
-  if (p == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t ph = 0;
   float q[8];
   const float *qrow = nullptr;
@@ -427,25 +512,25 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
   }
   // normal-head weight gradients are reduced on the CUDA cores (tiny: 611 numbers), fp32 registers across tiles
   float g_n2 = 0.f, g_n0[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool t0 = p == 0;
+  const bool t0 = tid == 0;
   bool first = true;
   const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kTcTile;
     const bool valid = base + p < A.in.n_points;
-    tc_load_inputs(sm, A, base, p, valid);
+    tc_load_inputs<SRC>(sm, A, &F, tile, base, p, half, valid);
     float d_o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (valid) {
       for (int c = 0; c < A.C; ++c) d_o[c] = __ldg(dout + (base + p) * A.C + c);
       if (A.in.keep && A.in.keep[base + p] == 0) d_o[A.C - 1] = 0.f;            // run_nerf.py:66
     }
-    fence_async_smem(); fence_before_sync(); __syncthreads();
-    float sigma, nraw[3] = {0.f, 0.f, 0.f};
-    uint64_t h1_mask;
-    tc_forward<true>(sm, A, tmem, &bar, ph, p, warp, qrow, sigma, nraw, h1_mask);
+    PN_ROUND_SYNC();
+    float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
+    uint32_t h1_mask;
+    tc_forward<true>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, h1_mask);
 
-    // B0: cotangent tiles
-    {
+    // B0: cotangent tiles (half 0 owns the row-level values)
+    if (half == 0) {
       float v[8] = {d_o[0], d_o[1], d_o[2], 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       st_chunk(sm + TS::DOUT, chunk_off(p, 0, 2), v);
       st_chunk(sm + TS::DOUT, chunk_off(p, 1, 2), z);
@@ -463,7 +548,7 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
         st_chunk(sm + TS::DNR, chunk_off(p, 1, 2), z);
       }
     }
-    fence_async_smem(); fence_before_sync(); __syncthreads();
+    PN_ROUND_SYNC();
     // B1: dC2^T += A2c^T dOut ; dA2 = dOut C2 ; (normals) dNH = dNraw N2
     if (t0) {
       fence_after_sync();
@@ -473,31 +558,30 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
         issue(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false);
       mma_commit(&bar);
     }
-    if (A.normals && p < 99) {                     // dN2w[j][k] / dN2b[j] on the CUDA cores (needs NH before E1 overwrites it)
-      const int j = p < 96 ? p >> 5 : p - 96, k = p & 31;
+    if (A.normals && tid < 99) {                   // dN2w[j][k] / dN2b[j] on the CUDA cores (needs NH before E1 overwrites it)
+      const int j = tid < 96 ? tid >> 5 : tid - 96, k = tid & 31;
       float s = 0.f;
       for (int r = 0; r < kTcTile; ++r)
-        s += tile_elem(sm + TS::DNR, r, j, 2) * (p < 96 ? tile_elem(sm + TS::NH, r, k, 4) : 1.f);
+        s += tile_elem(sm + TS::DNR, r, j, 2) * (tid < 96 ? tile_elem(sm + TS::NH, r, k, 4) : 1.f);
       g_n2 += s;
     }
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    __syncthreads();                               // all NH reads above are done
-    epi_grad64(lane_addr + TM_D1, sm + TS::A2C, p, false, 0);
+    if (A.normals) __syncthreads();                // all NH reads above are done
+    epi_grad32(lane_addr + TM_D1, sm + TS::A2C, p, half, false, 0);
     if (A.normals) {
-      float v[32];
-      tmem_ld16(lane_addr + TM_DN, v);
-      tmem_ld16(lane_addr + TM_DN + 16, v + 16);
+      float v[16];
+      tmem_ld16(lane_addr + TM_DN + half * 16, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float a[8];
-        ld_chunk(sm + TS::NH, chunk_off(p, c, 4), a);
+        ld_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[8 * c + j] = a[j] > 0.f ? v[8 * c + j] : 0.f;
-        st_chunk(sm + TS::NH, chunk_off(p, c, 4), v + 8 * c);
+        st_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), v + 8 * c);
       }
     }
-    fence_async_smem(); fence_before_sync(); __syncthreads();
+    PN_ROUND_SYNC();
     // B2: dC1 += dA2pre^T A1c ; dA1 = dA2pre C1
     if (t0) {
       fence_after_sync();
@@ -505,8 +589,8 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
       issue(tmem + TM_D1, k_major(sm + TS::A2C, 64), mn_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 1), 4, false);
       mma_commit(&bar);
     }
-    if (A.normals) {                               // dN0w[j][k] (k < 15) and dN0b[j] (k == 15): 4 outputs per thread
-      const int j = p >> 2, k0 = (p & 3) * 4;
+    if (A.normals && tid < 128) {                  // dN0w[j][k] (k < 15) and dN0b[j] (k == 15): 4 outputs per thread
+      const int j = tid >> 2, k0 = (tid & 3) * 4;
       for (int r = 0; r < kTcTile; ++r) {
         const float d = tile_elem(sm + TS::NH, r, j, 4);
 #pragma unroll
@@ -515,8 +599,8 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
       }
     }
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    epi_grad64(lane_addr + TM_D1, sm + TS::A1C, p, false, 0);
-    fence_async_smem(); fence_before_sync(); __syncthreads();
+    epi_grad32(lane_addr + TM_D1, sm + TS::A1C, p, half, false, 0);
+    PN_ROUND_SYNC();
     // B3: dC0 += dA1pre^T CIN ; dCIN = dA1pre C0 ; (normals) dgeo_n = dNHpre N0
     if (t0) {
       fence_after_sync();
@@ -527,10 +611,8 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
       mma_commit(&bar);
     }
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    {
-      float g[17];
-      tmem_ld16(lane_addr + TM_D1 + 16, g + 1);      // dCIN[16..32) = dgeo[0..15) + pad
-      if (dsh) {
+    if (half == 0) {
+      if (dsh) {                                       // dCIN[0..16) = d SH
         float v[16];
         tmem_ld16(lane_addr + TM_D1, v);
         tmem_ld_wait();
@@ -540,6 +622,9 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
           for (int c = 0; c < 4; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
       }
+    } else {
+      float g[17];
+      tmem_ld16(lane_addr + TM_D1 + 16, g + 1);        // dCIN[16..32) = dgeo[0..15) + pad
       tmem_ld_wait();
       if (A.normals) {
         float v[16];
@@ -548,11 +633,11 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
 #pragma unroll
         for (int j = 0; j < 15; ++j) g[1 + j] += v[j];
       }
-      g[0] = d_o[3];                                 // dsigma (keep mask applied above when C == 4)
+      g[0] = d_o[3];                                   // dsigma (keep mask applied above when C == 4)
       st_chunk(sm + TS::DH2, chunk_off(p, 0, 2), g);
       st_chunk(sm + TS::DH2, chunk_off(p, 1, 2), g + 8);
     }
-    fence_async_smem(); fence_before_sync(); __syncthreads();
+    PN_ROUND_SYNC();
     // B4: dS1^T += H1^T dH2 ; dH1 = dH2 S1
     if (t0) {
       fence_after_sync();
@@ -561,8 +646,8 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
       mma_commit(&bar);
     }
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    epi_grad64(lane_addr + TM_D1, sm + TS::A1, p, true, h1_mask);
-    fence_async_smem(); fence_before_sync(); __syncthreads();
+    epi_grad32(lane_addr + TM_D1, sm + TS::A1, p, half, true, h1_mask);
+    PN_ROUND_SYNC();
     // B5: dS0 += dH1pre^T X ; dX = dH1pre S0
     if (t0) {
       fence_after_sync();
@@ -572,14 +657,24 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
     }
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
     {
-      float v[32];
-      tmem_ld16(lane_addr + TM_D1, v);
-      tmem_ld16(lane_addr + TM_D1 + 16, v + 16);
+      float v[16];
+      tmem_ld16(lane_addr + TM_D1 + half * 16, v);
       tmem_ld_wait();
-      if (valid) {
-        float4 *o = reinterpret_cast<float4 *>(dfeat + (base + p) * dfeat_stride);
+      if (SRC == SRC_TILE) {
+        // fused scatter: this thread's 16 columns are levels 8*half .. 8*half+7 of its point; the warp's 32 lanes
+        // are 32 consecutive samples, so the run-aggregated scatter applies unchanged
+        float xv[3] = {0.f, 0.f, 0.f};
+        if (valid) { xv[0] = __ldg(F.pts + 3 * (base + p)); xv[1] = __ldg(F.pts + 3 * (base + p) + 1); xv[2] = __ldg(F.pts + 3 * (base + p) + 2); }
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int l = half * 8 + i;
+          if (l < F.G.n_levels)
+            scatter_level<false>(F.G, F.D.t[l], l, xv, valid ? v[2 * i] : 0.f, valid ? v[2 * i + 1] : 0.f, lane);
+        }
+      } else if (valid) {
+        float4 *o = reinterpret_cast<float4 *>(dfeat + (base + p) * dfeat_stride + half * 16);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        for (int c = 0; c < 4; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
     }
     first = false;
@@ -587,18 +682,20 @@ mlp_tc_bwd_kernel(const TcArgs A, const float *__restrict__ dout, float *__restr
   }
   // flush the weight gradients (every MMA has completed: the last commit was waited on)
   fence_after_sync();
-  const bool owner = lane < 16;
-  const int row = warp * 16 + lane;
-  if (!first) {
+  if (!first && warp < 4) {
+    const bool owner = lane < 16;
+    const int row = warp * 16 + lane;
     flush_acc(lane_addr + TM_GC1, 64, owner, row, G.c1, 64, 64, 64, false);
     flush_acc(lane_addr + TM_GS0, 32, owner, row, G.s0, 32, 64, 32, false);
     flush_acc(lane_addr + TM_GC0, 32, owner, row, G.c0, 31, 64, 31, false);
     flush_acc(lane_addr + TM_GS1, 16, owner, row, G.s1, 64, 64, 16, true);
     flush_acc(lane_addr + TM_GC2, 16, owner, row, G.c2, 64, 64, 3, true);
-    if (A.normals) {
-      if (p < 96 && G.n2w) atomicAdd(G.n2w + (p >> 5) * 32 + (p & 31), g_n2);
-      else if (p < 99 && G.n2b) atomicAdd(G.n2b + (p - 96), g_n2);
-      const int j = p >> 2, k0 = (p & 3) * 4;
+  }
+  if (!first && A.normals) {
+    if (tid < 96) { if (G.n2w) atomicAdd(G.n2w + (tid >> 5) * 32 + (tid & 31), g_n2); }
+    else if (tid < 99) { if (G.n2b) atomicAdd(G.n2b + (tid - 96), g_n2); }
+    if (tid < 128) {
+      const int j = tid >> 2, k0 = (tid & 3) * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (k0 + i < 15) { if (G.n0w) atomicAdd(G.n0w + j * 15 + k0 + i, g_n0[i]); }
@@ -635,6 +732,56 @@ namespace pn {
 int check_mlp_args(const pn_mlp_weights *w, const pn_mlp_input *in, bool *normals);   // mlp_fp32.cu
 }
 
+
+namespace pn {
+int check_grid_args(const pn_hash_grid *g);                                            // hash_encode.cu
+
+static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float *out, cudaStream_t st) {
+  // without the normal head the NH tile (last block of the forward map) is not allocated: 55.5 KB -> 4 CTAs/SM
+  const int smem = A.normals ? TS::FWD_END : TS::NH;
+  const int per_sm = (A.normals || fused) ? 3 : 4;       // x 128 TMEM columns each
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<4, SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
+    PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_fwd): %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  const int blocks = (int)(tiles < cap ? tiles : cap);
+  if (fused) mlp_tc_fwd_kernel<3, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  else if (A.normals) mlp_tc_fwd_kernel<3, SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  else mlp_tc_fwd_kernel<4, SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  count_launch();
+  return check_launch("mlp_tc_fwd_kernel");
+}
+
+static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const float *dout, float *dfeat,
+                         int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads &dw, cudaStream_t st) {
+  const int smem = TS::BWD_END;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
+  const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
+  const int64_t cap = (int64_t)sm_count() * 2;          // 2 CTAs/SM: 2 x 256 TMEM columns, 2 x 107 KB smem
+  const int blocks = (int)(tiles < cap ? tiles : cap);
+  if (fused) mlp_tc_bwd_kernel<SRC_TILE><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
+  else mlp_tc_bwd_kernel<SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
+  count_launch();
+  return check_launch("mlp_tc_bwd_kernel");
+}
+}  // namespace pn
+
 extern "C" int pn_mlp_fwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, float *out, pn_stream_t stream) {
   bool normals = false;
   if (int e = check_mlp_args(w, in, &normals)) return e;
@@ -643,21 +790,8 @@ extern "C" int pn_mlp_fwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, 
   TcArgs A;
   A.w = *w; A.in = *in; A.normals = normals; A.C = normals ? 7 : 4;
   PN_REQUIRE(A.C == 7 || ((uintptr_t)out & 15) == 0, PN_EINVAL, "out must be 16-byte aligned");
-  const int smem = TS::FWD_END;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_fwd): %s", cudaGetErrorString(e));
-    attr_set[dev] = true;
-  }
-  const int64_t tiles = ceil_div(in->n_points, kTcTile);
-  const int64_t cap = (int64_t)sm_count() * 3;          // 3 CTAs/SM: 3 x 128 TMEM columns, 3 x 63 KB smem
-  const int blocks = (int)(tiles < cap ? tiles : cap);
-  mlp_tc_fwd_kernel<<<blocks, kTcTile, smem, as_stream(stream)>>>(A, out);
-  count_launch();
-  return check_launch("mlp_tc_fwd_kernel");
+  FieldArgs F = {};
+  return launch_tc_fwd(A, F, false, out, as_stream(stream));
 }
 
 extern "C" int pn_mlp_bwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, const float *dout, float *dfeat,
@@ -674,19 +808,69 @@ extern "C" int pn_mlp_bwd_bf16(const pn_mlp_weights *w, const pn_mlp_input *in, 
   if (in->n_points == 0) return 0;
   TcArgs A;
   A.w = *w; A.in = *in; A.normals = normals; A.C = normals ? 7 : 4;
-  const int smem = TS::BWD_END;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
-    attr_set[dev] = true;
+  FieldArgs F = {};
+  return launch_tc_bwd(A, F, false, dout, dfeat, dfeat_stride, dsh, dsh_stride, *dw, as_stream(stream));
+}
+
+static int fill_field(FieldArgs &F, const pn_hash_grid *grid, const float *const *tables, float *const *dtables,
+                      const float *pts, const float *qparams) {
+  if (int e = check_grid_args(grid)) return e;
+  PN_REQUIRE(grid->n_levels == 16, PN_ESHAPE, "the fused field kernels are built for 16 levels (32 features), got %d",
+             grid->n_levels);
+  PN_REQUIRE(pts != nullptr, PN_EINVAL, "pts is NULL");
+  F.G = make_grid_dev(*grid);
+  for (int l = 0; l < PN_MAX_LEVELS; ++l) {
+    F.T.t[l] = tables ? reinterpret_cast<const float2 *>(tables[l]) : nullptr;
+    F.D.t[l] = dtables ? reinterpret_cast<float2 *>(dtables[l]) : nullptr;
+    PN_REQUIRE(!tables || tables[l], PN_EINVAL, "tables[%d] is NULL", l);
+    PN_REQUIRE(!dtables || dtables[l], PN_EINVAL, "dtables[%d] is NULL", l);
   }
-  const int64_t tiles = ceil_div(in->n_points, kTcTile);
-  const int64_t cap = (int64_t)sm_count() * 2;          // 2 CTAs/SM: 2 x 256 TMEM columns, 2 x 107 KB smem
-  const int blocks = (int)(tiles < cap ? tiles : cap);
-  mlp_tc_bwd_kernel<<<blocks, kTcTile, smem, as_stream(stream)>>>(A, dout, dfeat, dfeat_stride, dsh, dsh_stride, *dw);
-  count_launch();
-  return check_launch("mlp_tc_bwd_kernel");
+  F.pts = pts;
+  F.qparams = qparams;
+  return 0;
+}
+
+extern "C" int pn_field_fwd_bf16(const pn_hash_grid *grid, const float *const *tables, const float *qparams,
+                                 const pn_mlp_weights *w, const float *pts, const float *dirs, int samples_per_ray,
+                                 const float *act_q, int64_t n_points, float *out, uint8_t *keep, void *feat_tiles,
+                                 pn_stream_t stream) {
+  PN_REQUIRE(w && tables && dirs && out, PN_EINVAL, "NULL pointer argument");
+  pn_mlp_input in = {};
+  in.feat = pts;            // placeholder so that the shared argument check passes; the fused kernel never reads it
+  in.feat_stride = 32;
+  in.dirs = dirs; in.samples_per_ray = samples_per_ray; in.act_q = act_q; in.n_points = n_points;
+  bool normals = false;
+  PN_REQUIRE(((uintptr_t)pts & 15) == 0, PN_EINVAL, "pts must be 16-byte aligned");
+  if (int e = check_mlp_args(w, &in, &normals)) return e;
+  if (n_points == 0) return 0;
+  TcArgs A;
+  A.w = *w; A.in = in; A.normals = normals; A.C = normals ? 7 : 4;
+  PN_REQUIRE(A.C == 7 || ((uintptr_t)out & 15) == 0, PN_EINVAL, "out must be 16-byte aligned");
+  FieldArgs F = {};
+  if (int e = fill_field(F, grid, tables, nullptr, pts, qparams)) return e;
+  F.keep_out = keep;
+  F.featb = reinterpret_cast<uint4 *>(feat_tiles);
+  PN_REQUIRE(((uintptr_t)feat_tiles & 15) == 0, PN_EINVAL, "feat_tiles must be 16-byte aligned");
+  return launch_tc_fwd(A, F, true, out, as_stream(stream));
+}
+
+extern "C" int pn_field_bwd_bf16(const pn_hash_grid *grid, float *const *dtables, const pn_mlp_weights *w,
+                                 const void *feat_tiles, const float *pts, const float *dirs, int samples_per_ray,
+                                 const float *act_q, const uint8_t *keep, const float *dout, int64_t n_points,
+                                 const pn_mlp_grads *dw, pn_stream_t stream) {
+  PN_REQUIRE(w && dtables && dirs && dout && dw && feat_tiles, PN_EINVAL, "NULL pointer argument");
+  pn_mlp_input in = {};
+  in.feat = pts;
+  in.feat_stride = 32;
+  in.dirs = dirs; in.samples_per_ray = samples_per_ray; in.act_q = act_q; in.keep = keep; in.n_points = n_points;
+  bool normals = false;
+  PN_REQUIRE(((uintptr_t)pts & 15) == 0 && ((uintptr_t)feat_tiles & 15) == 0, PN_EINVAL, "pts / feat_tiles alignment");
+  if (int e = check_mlp_args(w, &in, &normals)) return e;
+  if (n_points == 0) return 0;
+  TcArgs A;
+  A.w = *w; A.in = in; A.normals = normals; A.C = normals ? 7 : 4;
+  FieldArgs F = {};
+  if (int e = fill_field(F, grid, nullptr, dtables, pts, nullptr)) return e;
+  F.featb = reinterpret_cast<uint4 *>(const_cast<void *>(feat_tiles));
+  return launch_tc_bwd(A, F, true, dout, nullptr, 32, nullptr, 16, *dw, as_stream(stream));
 }

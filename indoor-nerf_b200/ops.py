@@ -284,9 +284,28 @@ class FieldFn(torch.autograd.Function):
         pts = fcontig(pts)
         dirs = fcontig(viewdirs)
         w = {k: fcontig(t.detach()) for k, t in zip(keys, weights)}
-        feat, keep = hash_encode_fwd(grid, [t.detach() for t in tables], pts, qparams)
         ctx.mode = _MLP_MODE
-        out = mlp_fwd(w, feat, dirs=dirs, samples_per_ray=S, act_q=act_q, keep=keep, mode=ctx.mode)
+        ctx.fused = ctx.mode == "bf16" and grid.n_levels == 16
+        if ctx.fused:
+            # one kernel: hash encode -> SH -> NeRFSmall (tcgen05) -> keep mask; features saved as bf16 operand tiles
+            P = pts.shape[0]
+            C = 7 if w.get("n0w") is not None else 4
+            out = torch.empty((P, C), dtype=torch.float32, device=pts.device)
+            keep = torch.empty((P,), dtype=torch.bool, device=pts.device)
+            need_bwd = any(t.requires_grad for t in params)
+            feat = torch.empty(((P + 127) // 128) * 8192, dtype=torch.uint8, device=pts.device) if need_bwd else None
+            _check_tables(grid, tables)
+            with _guard(pts):
+                ws = _weights_struct(w)
+                call("pn_field_fwd_bf16", ctypes.byref(grid), _ptr_array([t.detach() for t in tables]),
+                     dptr(qparams, allow_none=True), ctypes.byref(ws), dptr(pts), dptr(dirs), int(S),
+                     dptr(act_q, allow_none=True), P, dptr(out), dptr(keep, torch.bool),
+                     dptr(feat, torch.uint8, allow_none=True), stream())
+            if feat is None:
+                feat = torch.empty(0, dtype=torch.uint8, device=pts.device)
+        else:
+            feat, keep = hash_encode_fwd(grid, [t.detach() for t in tables], pts, qparams)
+            out = mlp_fwd(w, feat, dirs=dirs, samples_per_ray=S, act_q=act_q, keep=keep, mode=ctx.mode)
         ctx.grid, ctx.S, ctx.act_q, ctx.keys, ctx.n_tables = grid, S, act_q, keys, n_tables
         ctx.save_for_backward(pts, dirs, feat, keep, *params)
         return out
@@ -296,6 +315,17 @@ class FieldFn(torch.autograd.Function):
         pts, dirs, feat, keep, *params = ctx.saved_tensors
         tables, weights = params[:ctx.n_tables], params[ctx.n_tables:]
         w = {k: fcontig(t.detach()) for k, t in zip(ctx.keys, weights)}
+        if ctx.fused:
+            # one kernel: NeRFSmall backward (tcgen05) + run-aggregated scatter into the flat table gradient
+            dout = fcontig(dout)
+            flat = torch.zeros((ctx.n_tables,) + tuple(tables[0].shape), dtype=torch.float32, device=pts.device)
+            dw = {k: torch.zeros_like(w[k]) for k in _MLP_KEYS if w.get(k) is not None}
+            with _guard(pts):
+                ws, gs = _weights_struct(w), _weights_struct(dw)
+                call("pn_field_bwd_bf16", ctypes.byref(ctx.grid), _ptr_array(list(flat.unbind(0))), ctypes.byref(ws),
+                     dptr(feat, torch.uint8), dptr(pts), dptr(dirs), int(ctx.S), dptr(ctx.act_q, allow_none=True),
+                     dptr(keep, torch.bool), dptr(dout), pts.shape[0], ctypes.byref(gs), stream())
+            return (None,) * 8 + tuple(flat.unbind(0)) + tuple(dw[k] for k in ctx.keys)
         dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep, mode=ctx.mode)
         tgrads = [None] * ctx.n_tables
         if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):

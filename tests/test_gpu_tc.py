@@ -213,3 +213,57 @@ def test_every_gemm_shape_of_the_mlp(case):
     err = _shape_case(*case)
     print(case, "rel err", err)
     assert err < 1e-3, (case, err)
+
+
+def test_fused_field_kernels_match_unfused():
+    """pn_field_fwd/bwd_bf16 (hash + SH + MLP in one kernel; MLP backward + scatter in one kernel) against the
+    unfused bf16 path (hash kernel -> fp32 features -> pn_mlp_*_bf16 -> dfeat -> hash scatter kernel)."""
+    import numpy as np
+    import indoor_nerf_b200 as pn
+    from oracle.fixtures import mlp_weights, synthetic_tables
+    N, S = 700, 64
+    box = (torch.tensor([-3.0, -3.2, -2.9]), torch.tensor([3.1, 3.0, 3.3]))
+    for normals in (False, True):
+        emb = pn.HashEmbedder(box, log2_hashmap_size=15).cuda()
+        with torch.no_grad():
+            emb.table_storage.copy_(torch.from_numpy(synthetic_tables(16, 15, amp=0.3, salt=3)))
+        w = mlp_weights(11, normals)
+        net = pn.NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, input_ch=32,
+                           input_ch_views=16, predict_normals=normals).cuda()
+        with torch.no_grad():
+            net.sigma_net[0].weight.copy_(w["s0"]); net.sigma_net[1].weight.copy_(w["s1"])
+            net.color_net[0].weight.copy_(w["c0"]); net.color_net[1].weight.copy_(w["c1"]); net.color_net[2].weight.copy_(w["c2"])
+            if normals:
+                net.normal_net[0].weight.copy_(w["n0w"]); net.normal_net[0].bias.copy_(w["n0b"])
+                net.normal_net[2].weight.copy_(w["n2w"]); net.normal_net[2].bias.copy_(w["n2b"])
+        gen = torch.Generator(device="cuda").manual_seed(4)
+        pts = (torch.rand(N, S, 3, device="cuda", generator=gen) - 0.5) * 7.0      # some points fall outside the box
+        dirs = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda", generator=gen), dim=-1)
+        dout = torch.randn(N, S, 7 if normals else 4, device="cuda", generator=gen)
+        sh = pn.SHEncoder()
+        results = []
+        for fused in (True, False):
+            for q in list(emb.parameters()) + list(net.parameters()):
+                q.grad = None
+            pn.set_mlp_mode("bf16")
+            try:
+                if fused:
+                    out = pn.run_network(pts, dirs, net, emb, sh)
+                else:
+                    feat, keep = emb(pts.reshape(-1, 3))
+                    keys, weights = net.kernel_weights()
+                    x = torch.cat([feat, sh(dirs[:, None].expand(N, S, 3).reshape(-1, 3))], -1)
+                    out = pn.ops.MlpFn.apply(x, None, keys, *weights)
+                    mask = torch.ones_like(out); mask[~keep, -1] = 0
+                    out = (out * mask).reshape(N, S, -1)
+                (out * dout).sum().backward()
+            finally:
+                pn.set_mlp_mode("fp32")
+            results.append((out.detach(), [e.weight.grad.clone() for e in emb.embeddings],
+                            [q.grad.clone() for q in net.parameters()]))
+        (o1, t1, w1), (o2, t2, w2) = results
+        assert _rel(o1, o2)[0] < 2e-3, ("fused forward", _rel(o1, o2))        # features are bf16-rounded once in both
+        for l in (0, 5, 10, 15):
+            assert _rel(t1[l], t2[l])[0] < 2e-2, ("table grad level %d" % l, _rel(t1[l], t2[l]))
+        for a, b in zip(w1, w2):
+            assert _rel(a, b)[0] < 2e-2, ("weight grad", _rel(a, b))
