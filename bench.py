@@ -27,6 +27,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+MLP_MODE = os.environ.get("POCKETNERF_MLP", "bf16")     # "bf16": tcgen05 tensor-core NeRFSmall (north_star's 2e-3 mode); "fp32": FFMA
 RAYS_PER_RANK = 65536
 N_SAMPLES, N_IMPORTANCE = 64, 128
 HASH_BYTES_PER_POINT = 12 + 16 * 8 * 2 * 4 + 16 * 2 * 4      # 1164 B/point
@@ -179,6 +180,7 @@ def run_ours(args):
     from indoor_nerf_b200 import _lib, model as pmodel, ops, synthetic
     from indoor_nerf_b200.trainer import Trainer
 
+    pn.set_mlp_mode(MLP_MODE)
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -219,7 +221,9 @@ def run_ours(args):
     line = {
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "vs_baseline": None,
+        "dtype": "bf16 NeRFSmall on tcgen05 (fp32 accumulate) + f32 hash grid / compositing / sampling" if MLP_MODE == "bf16"
+        else "f32", "data": "synthetic", "config": workload_config(world),
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -267,6 +271,60 @@ def run_ours(args):
                             "ms_per_launch": t_fwd,
                             "backward": {"kernel": "hash_bwd_kernel", "ms_per_launch": t_bwd,
                                          "achieved": HASH_BYTES_PER_POINT * P / (t_bwd * 1e-3) / 1e9}}
+        line["roofline"]["traffic"] = 1.890e9 if P == 12582912 else None   # ncu dram bytes read+write per launch (profiles/r01_ncu_full_hash_fwd_mlp_fwd_fp32.csv)
+        # ---- the fused field kernels of the bf16 mode (what the training step actually launches) ---------
+        if MLP_MODE == "bf16":
+            try:
+                r, t = pool_dev[0]
+                z = torch.sort(2.0 + 4.0 * torch.rand(RAYS_PER_RANK, N_SAMPLES + N_IMPORTANCE, device=dev), -1)[0]
+                pts3 = ops.make_points(r[0], r[1], z)
+                vd = r[1] / r[1].norm(dim=-1, keepdim=True)
+                net = kw_train["network_fine"]
+                sh = pn.SHEncoder()
+                fw, bw = [], []
+                for it in range(6):
+                    torch.cuda.synchronize()
+                    e0.record()
+                    out = pn.run_network(pts3, vd, net, embed, sh)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    fw.append(e0.elapsed_time(e1))
+                    dout = torch.randn_like(out)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    out.backward(dout)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    bw.append(e0.elapsed_time(e1))
+                tf, tb = float(np.median(fw[2:])), float(np.median(bw[2:]))
+                tf_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0) \
+                    if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+                line["fused_kernels"] = {
+                    "points_per_launch": P,
+                    "field_fwd": {"kernel": "mlp_tc_fwd_kernel<3,SRC_HASH>", "ms": tf,
+                                  "hbm_algorithmic_GBs": (12 + 1024 + 16 + 64 + 1) * P / (tf * 1e-3) / 1e9,
+                                  "tensor_TFLOPs": 18688 * P / (tf * 1e-3) / 1e12, "tensor_frac": 18688 * P / (tf * 1e-3) / 1e12 / tf_peak},
+                    "field_bwd": {"kernel": "mlp_tc_bwd_kernel<SRC_TILE> (+ torch memset/adds of the autograd node)", "ms": tb,
+                                  "hbm_algorithmic_GBs": (12 + 64 + 16 + 1 + 1024) * P / (tb * 1e-3) / 1e9,
+                                  "tensor_TFLOPs": 56064 * P / (tb * 1e-3) / 1e12, "tensor_frac": 56064 * P / (tb * 1e-3) / 1e12 / tf_peak},
+                    "note": "latency/L2-atomic bound, not HBM or tensor bound: see DESIGN.md §4 and profiles/"}
+                del pts3, z, out, dout
+                for prm in list(embed.parameters()) + list(net.parameters()):
+                    prm.grad = None
+            except Exception as ex:
+                line["fused_kernels"] = {"error": repr(ex)}
+            # the same training step in the fp32 (FFMA, 1e-5 parity) mode
+            try:
+                pn.set_mlp_mode("fp32")
+                for i in range(2):
+                    step_resident(i)
+                ms32 = time_steps(step_resident, 3, 1)
+                line["fp32_mode"] = {"value": RAYS_PER_RANK * 3 / (ms32 / 1e3), "unit": "rays/s", "ms_per_step": ms32 / 3,
+                                     "what": "same step with the fp32 FFMA NeRFSmall kernels and unfused hash kernels"}
+            except Exception as ex:
+                line["fp32_mode"] = {"error": repr(ex)}
+            finally:
+                pn.set_mlp_mode(MLP_MODE)
         # ---- config 2: full 800x800 test-view render, finest_res 1024 -----------------------------------
         try:
             scene2 = synthetic.blender_scene(800, 800, n_views=8)
