@@ -559,3 +559,110 @@ def test_radam_fused(pn, golden):
     close(st["exp_avg"], 0.1 * flat[3], 1e-6, "flat first moment")
     step_size = 1.0 / (1 - 0.9)
     close(emb.embeddings[3].weight, ref[3] - 1e-2 * step_size * 0.1 * flat[3], 1e-5, "sgd-degenerated first step")
+
+
+# ------------------------------------------------------------------------------------------------------
+# BASELINE configs[3] and configs[4] at small ray counts (parity cases, not bench lines)
+# ------------------------------------------------------------------------------------------------------
+def test_config_scannet_shape_normals_t22(pn):
+    """ScanNet-shaped: log2_hashmap 22 (512 MiB of tables), near 0.1 / far 10, fine AND coarse net with the normal
+    head, depth / normal maps consumed by a loss (as the structural priors do) -> gradients through
+    depth_map and normal_map.  Against the oracle on the GPU, identical parameters and draws."""
+    torch.manual_seed(3)
+    box = (np.array([-4.1, -3.2, -1.0], np.float32), np.array([4.3, 3.1, 3.4], np.float32))
+    log2T = 22
+    emb = pn.HashEmbedder((T(box[0]), T(box[1])), log2_hashmap_size=log2T, finest_resolution=512).cuda().train()
+    with torch.no_grad():
+        emb.table_storage.uniform_(-0.3, 0.3)
+    ws = [mlp_weights(51, True), mlp_weights(52, True)]
+    nets = [mlp_from(pn, w) for w in ws]
+    N = 1024
+    rs = np.random.RandomState(4)
+    o = (rs.rand(N, 3) * np.array([2.0, 2.0, 1.0]) + np.array([-1.0, -1.0, 1.0])).astype(np.float32)
+    d = rs.randn(N, 3).astype(np.float32)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    rays = cu(np.concatenate([o, d, np.full((N, 1), 0.1, np.float32), np.full((N, 1), 10.0, np.float32), d], -1))
+    t_rand, u = torch.rand(N, 64, device="cuda"), torch.rand(N, 128, device="cuda")
+    sh = pn.SHEncoder()
+    query = lambda inputs, viewdirs, fn: pn.run_network(inputs, viewdirs, fn, embed_fn=emb, embeddirs_fn=sh)
+    with _Rng([t_rand, u], []):
+        ret = pn.render_rays(rays, nets[0], query, 64, embed_fn=emb, retraw=True, perturb=1.0, N_importance=128,
+                             network_fine=nets[1], white_bkgd=False, predict_normals=True)
+    tabs = [e.weight.detach().clone().requires_grad_(True) for e in emb.embeddings]
+    wo = [{k: v.cuda().clone().requires_grad_(True) for k, v in w.items()} for w in ws]
+    res = O.level_resolutions(16, 512, device="cuda")
+    embed = lambda x: O.hash_embed(x, cu(box[0]), cu(box[1]), tabs, res, log2T)
+    q = [lambda pts, vd, w=w: O.run_network(pts, vd, embed, lambda x: O.nerf_small(x, w)) for w in wo]
+    ref = O.render_rays(rays, q[0], q[1], 64, 128, t_rand=t_rand, u=u, white_bkgd=False, predict_normals=True)
+    assert ret["raw"].shape == (N, 192, 7) and ret["normal_map"].shape == (N, 3)
+    for k in ["rgb0", "acc0", "depth0", "normal0"]:
+        close(ret[k], ref[k], 5e-5, k)
+    for k in ["rgb_map", "depth_map", "acc_map", "normal_map"]:
+        close_l2(ret[k], ref[k], 2e-3, k)
+    tgt = torch.rand(N, 3, device="cuda")
+    nrm = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda"), dim=-1)
+    lo = lambda r: ((r["rgb_map"] - tgt) ** 2).mean() + ((r["rgb0"] - tgt) ** 2).mean() \
+        + 0.1 * ((r["depth_map"] - 3.0) ** 2).mean() + 0.1 * (1 - (r["normal_map"] * nrm).sum(-1)).mean() \
+        + 0.1 * (1 - (r["normal0"] * nrm).sum(-1)).mean()
+    lo(ret).backward()
+    lo(ref).backward()
+    for l in (0, 7, 15):
+        close_l2(emb.embeddings[l].weight.grad, tabs[l].grad, 3e-2, "table grad level %d" % l)
+    for i, m in enumerate(nets):
+        for k, gr in mlp_grads(m).items():
+            close_l2(gr, wo[i][k].grad, 3e-2, "net%d d%s" % (i, k))
+
+
+def test_config_llff_ndc_quantized(pn):
+    """LLFF-shaped: NDC rays (near 0, far 1), lindisp off, 64+64 samples, raw noise, A-CAQ fake-quant on the
+    gathered embeddings and on the first sigma layer (weights + activations), learned per-level bit-widths.
+    Our fused quantisation against the oracle's lbq_* restatement with the same calibration."""
+    torch.manual_seed(5)
+    H, W, focal = 378, 504, 407.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = torch.tensor([[1.0, 0, 0, 0.1], [0, 1, 0, -0.05], [0, 0, 1, 0.2]])
+    ro, rd = pn.get_rays(H, W, K, c2w)
+    oro, ord_ = O.get_rays(H, W, K, c2w.cuda())
+    close(rd, ord_, 1e-6, "rays_d")
+    no, nd = pn.ndc_rays(H, W, focal, 1.0, ro, rd)
+    ono, ond = O.ndc_rays(H, W, focal, 1.0, ro, rd)
+    close(no, ono, 1e-6, "ndc o"); close(nd, ond, 1e-6, "ndc d")
+    sel = torch.randperm(H * W, device="cuda")[:512]
+    o, d = no.reshape(-1, 3)[sel], nd.reshape(-1, 3)[sel]
+    vd = torch.nn.functional.normalize(rd.reshape(-1, 3)[sel], dim=-1)
+    N = o.shape[0]
+    rays = torch.cat([o, d, torch.zeros(N, 1, device="cuda"), torch.ones(N, 1, device="cuda"), vd], -1)
+    box = (torch.tensor([-1.6, -1.3, -1.0001]), torch.tensor([1.6, 1.3, 1.0001]))
+    emb = pn.HashEmbedder(box, log2_hashmap_size=16, use_quantization=True, quantization_bits=8).cuda()
+    with torch.no_grad():
+        emb.table_storage.uniform_(-0.5, 0.5)
+        for l, qz in enumerate(emb.quantizers):
+            qz.soft_bits.fill_(4.0 + 0.5 * l)
+    emb.current_step = 10_000
+    emb.train()
+    w = mlp_weights(61)
+    net = mlp_from(pn, w, use_quantization=True, quantization_bits=8).train()
+    sh = pn.SHEncoder()
+    t_rand, u = torch.rand(N, 64, device="cuda"), torch.rand(N, 64, device="cuda")
+    n0, n1 = torch.randn(N, 64, device="cuda"), torch.randn(N, 128, device="cuda")
+    query = lambda inputs, viewdirs, fn: pn.run_network(inputs, viewdirs, fn, embed_fn=emb, embeddirs_fn=sh)
+    with _Rng([t_rand, u], [n0, n1]):
+        ret = pn.render_rays(rays, net, query, 64, embed_fn=emb, retraw=True, perturb=1.0, N_importance=64,
+                             network_fine=net, white_bkgd=False, raw_noise_std=1.0)
+    assert all(qz.calibrated for qz in emb.quantizers) and net.sigma_act_quantizers[0].calibrated
+    # oracle with the calibration our modules arrived at (the calibration itself is checked in test_hash_quant_golden)
+    tabs = [e.weight.detach() for e in emb.embeddings]
+    res = O.level_resolutions(16, 512, device="cuda")
+    quant = [O.lbq_scalars(qz.soft_bits.data, qz.range_scale.data, qz.v_max.data, False, True) + (True,) for qz in emb.quantizers]
+    bmin, bmax = box[0].cuda(), box[1].cuda()
+    embed = lambda x: O.hash_embed(x, bmin, bmax, tabs, res, 16, quant=quant)
+    wq, aq = net.sigma_weight_quantizer, net.sigma_act_quantizers[0]
+    mq = dict(weight=O.lbq_scalars(wq.soft_bits.data, wq.range_scale.data, None, True, True) + (True,),
+              act=O.lbq_scalars(aq.soft_bits.data, aq.range_scale.data, aq.v_max.data, False, True) + (True,))
+    wd = {k: v.cuda() for k, v in w.items()}
+    q = lambda pts, vdd: O.run_network(pts, vdd, embed, lambda x: O.nerf_small(x, wd, quant=mq))
+    ref = O.render_rays(rays, q, q, 64, 64, t_rand=t_rand, u=u, noise0=n0, noise1=n1, white_bkgd=False)
+    for k in ["rgb0", "acc0", "depth0"]:
+        close(ret[k], ref[k], 5e-5, k)
+    for k in ["rgb_map", "acc_map", "raw"]:
+        close_l2(ret[k], ref[k], 2e-3, k)
