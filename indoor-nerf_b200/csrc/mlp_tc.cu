@@ -739,6 +739,8 @@ int check_grid_args(const pn_hash_grid *g);                                     
 static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float *out, cudaStream_t st) {
   // without the normal head the NH tile (last block of the forward map) is not allocated: 55.5 KB -> 4 CTAs/SM
   const int smem = A.normals ? TS::FWD_END : TS::NH;
+  // the fused variant carries the hash-gather state: at 4 CTAs/SM (64 registers) it spills and measured 25 %
+  // slower than at 3 CTAs/SM (76 registers), so it stays at 3
   const int per_sm = (A.normals || fused) ? 3 : 4;       // x 128 TMEM columns each
   static bool attr_set[64] = {false};
   int dev = 0;
