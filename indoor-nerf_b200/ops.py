@@ -114,6 +114,51 @@ def hash_gather_minmax(grid, tables, x):
     return mm
 
 
+# ---------------------------------------------------------------------------------------------------
+# table gradients: one persistent flat [L,T,2] buffer installed as the tables' .grad
+# ---------------------------------------------------------------------------------------------------
+# Each table has up to three gradient producers per step (coarse field, fine field, TV loss).  If every
+# producer returned its own dense [T,2] gradients, the autograd engine would sum them out of place (views of
+# a shared buffer cannot be accumulated in place in its input buffers): three 64 MiB memsets, 32 add launches
+# and — worse — 16 unrelated result tensors, so the optimiser and the data-parallel all-reduce could no longer
+# treat the table gradient as ONE buffer.  Instead the backward kernels accumulate (atomics) straight into a
+# flat buffer whose per-level views ARE the parameters' .grad (the "main grad" pattern), and the autograd nodes
+# return None for the tables.  Gradients that other producers already delivered to .grad are folded in first;
+# optimizer.zero_grad() (set_to_none) is respected because the buffer is re-zeroed whenever .grad is found None.
+# Consequence: use loss.backward() (as the reference does); torch.autograd.grad() w.r.t. the tables sees None.
+_FLAT_GRADS = {}
+
+
+def table_grad_buffer(tables):
+    """The flat gradient buffer of `tables` with every level's view installed as .grad (zeroed / seeded as needed)."""
+    t0 = tables[0]
+    L = len(tables)
+    key = (t0.data_ptr(), L, tuple(t0.shape), str(t0.device))
+    flat = _FLAT_GRADS.get(key)
+    if flat is None:
+        if len(_FLAT_GRADS) > 8:
+            _FLAT_GRADS.clear()
+        flat = torch.empty((L,) + tuple(t0.shape), dtype=torch.float32, device=t0.device)
+        _FLAT_GRADS[key] = flat
+        installed = [False] * L
+    else:
+        installed = [t.grad is not None and t.grad.data_ptr() == flat[l].data_ptr() for l, t in enumerate(tables)]
+    if not all(installed):
+        if all(t.grad is None for t in tables):
+            flat.zero_()
+        else:
+            for l, t in enumerate(tables):
+                if installed[l]:
+                    continue
+                if t.grad is None:
+                    flat[l].zero_()
+                else:
+                    flat[l].copy_(t.grad)
+        for l, t in enumerate(tables):
+            t.grad = flat[l]
+    return flat
+
+
 class HashEncodeFn(torch.autograd.Function):
     """feat, keep = HashEncodeFn.apply(x, grid, qparams, *tables).  Gradients flow to the tables only:
     sample positions never require grad on this path (z_samples is detached, run_nerf.py:510)."""
@@ -129,12 +174,10 @@ class HashEncodeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat, _dkeep):
         x, *tables = ctx.saved_tensors
-        grads = [None] * len(tables)
         if dfeat is not None and any(ctx.needs_input_grad[3:]):
-            flat = torch.zeros((len(tables),) + tuple(tables[0].shape), dtype=torch.float32, device=x.device)
+            flat = table_grad_buffer(tables)
             hash_encode_bwd(ctx.grid, list(flat.unbind(0)), x, dfeat)
-            grads = [flat[l] if ctx.needs_input_grad[3 + l] else None for l in range(len(tables))]
-        return (None, None, None) + tuple(grads)
+        return (None, None, None) + (None,) * len(tables)
 
 
 class TVLossFn(torch.autograd.Function):
@@ -159,12 +202,18 @@ class TVLossFn(torch.autograd.Function):
     def backward(ctx, dloss):
         mv, *tables = ctx.saved_tensors
         L = len(tables)
-        flat = torch.zeros((L,) + tuple(tables[0].shape), dtype=torch.float32, device=tables[0].device)
+        if len({t.data_ptr() for t in tables}) == L:
+            flat = table_grad_buffer(tables)
+            targets = list(flat.unbind(0))
+            ret = (None,) * L
+        else:                                   # the same tensor passed for several levels: plain dense gradients
+            targets = [torch.zeros_like(t) for t in tables]
+            ret = tuple(targets)
         cube = (ctypes.c_int32 * L)(*ctx.cubes)
-        with _guard(flat):
-            call("pn_tv_loss_bwd", _ptr_array([t.detach() for t in tables]), _ptr_array(list(flat.unbind(0))), L,
+        with _guard(tables[0]):
+            call("pn_tv_loss_bwd", _ptr_array([t.detach() for t in tables]), _ptr_array(targets), L,
                  ctx.log2T, cube, dptr(mv, torch.int64), dptr(fcontig(dloss)), stream())
-        return (None, None, None) + tuple(flat.unbind(0))
+        return (None, None, None) + ret
 
 
 def radam_step(p, g, m, v, beta1, beta2, eps, wd_lr, step_lr, mode):
@@ -275,8 +324,8 @@ class FieldFn(torch.autograd.Function):
     """raw[P, 4|7] = FieldFn.apply(pts[P,3], viewdirs[N,3], S, grid, qparams, act_q, keys, n_tables,
     *tables, *weights): hash encode -> SH -> NeRFSmall -> keep-mask, i.e. run_network
     (run_nerf.py:53-68) as one autograd node.  The feature tensor is kept for the backward; the table
-    gradients come out as views of one flat [L,T,2] buffer so that data-parallel training can
-    all-reduce them in one call."""
+    gradients are accumulated into the flat buffer installed as the tables' .grad (table_grad_buffer), so
+    data-parallel training all-reduces them in one call and RAdam updates them in one launch."""
 
     @staticmethod
     def forward(ctx, pts, viewdirs, S, grid, qparams, act_q, keys, n_tables, *params):
@@ -318,21 +367,22 @@ class FieldFn(torch.autograd.Function):
         if ctx.fused:
             # one kernel: NeRFSmall backward (tcgen05) + run-aggregated scatter into the flat table gradient
             dout = fcontig(dout)
-            flat = torch.zeros((ctx.n_tables,) + tuple(tables[0].shape), dtype=torch.float32, device=pts.device)
+            if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):
+                flat = table_grad_buffer(tables)
+            else:                               # frozen tables: the kernel still needs somewhere to scatter
+                flat = torch.zeros((ctx.n_tables,) + tuple(tables[0].shape), dtype=torch.float32, device=pts.device)
             dw = {k: torch.zeros_like(w[k]) for k in _MLP_KEYS if w.get(k) is not None}
             with _guard(pts):
                 ws, gs = _weights_struct(w), _weights_struct(dw)
                 call("pn_field_bwd_bf16", ctypes.byref(ctx.grid), _ptr_array(list(flat.unbind(0))), ctypes.byref(ws),
                      dptr(feat, torch.uint8), dptr(pts), dptr(dirs), int(ctx.S), dptr(ctx.act_q, allow_none=True),
                      dptr(keep, torch.bool), dptr(dout), pts.shape[0], ctypes.byref(gs), stream())
-            return (None,) * 8 + tuple(flat.unbind(0)) + tuple(dw[k] for k in ctx.keys)
+            return (None,) * (8 + ctx.n_tables) + tuple(dw[k] for k in ctx.keys)
         dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep, mode=ctx.mode)
-        tgrads = [None] * ctx.n_tables
         if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):
-            flat = torch.zeros((ctx.n_tables,) + tuple(tables[0].shape), dtype=torch.float32, device=pts.device)
+            flat = table_grad_buffer(tables)
             hash_encode_bwd(ctx.grid, list(flat.unbind(0)), pts, dfeat)
-            tgrads = list(flat.unbind(0))
-        return (None,) * 8 + tuple(tgrads) + tuple(dw[k] for k in ctx.keys)
+        return (None,) * (8 + ctx.n_tables) + tuple(dw[k] for k in ctx.keys)
 
 
 # ---------------------------------------------------------------------------------------------------
