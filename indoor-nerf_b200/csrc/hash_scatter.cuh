@@ -44,8 +44,11 @@ __device__ __forceinline__ void scatter_level(const HashGridDev &G, float2 *__re
   // end of this lane's run = next head above it
   const uint32_t above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));
   const int end = above ? (__ffs(above) - 1) : 32;
+  // only as many doubling steps as the longest run in this warp needs (coarse levels: 4-5, mid levels: 1-3)
+  const int maxlen = (int)__reduce_max_sync(0xffffffffu, (unsigned)(head ? end - lane : 0));
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
+    if (off >= maxlen) break;
     const bool take = (lane + off) < end;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
