@@ -94,7 +94,10 @@ def dist_setup(n):
     if world > 1:
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a rank-divergent code path must fail in minutes, not hold N GPUs for the
+        # default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=150))
         return dist.get_rank(), world, local
     return 0, 1, 0
 
@@ -146,7 +149,7 @@ def cpu_reference_steps(steps, warmup, rays_per_step, threads):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     threads = os.cpu_count() or 1
     total = args.steps + args.warmup
     rays = 1024 if total <= 16 else (256 if total <= 64 else 64)
@@ -162,7 +165,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    return line
 
 
 def workload_config(n):
@@ -313,17 +316,19 @@ def run_ours(args):
                     prm.grad = None
             except Exception as ex:
                 line["fused_kernels"] = {"error": repr(ex)}
-            # the same training step in the fp32 (FFMA, 1e-5 parity) mode
-            try:
+            # the same training step in the fp32 (FFMA, 1e-5 parity) mode.  Single-GPU runs only: Trainer.step
+            # all-reduces, and this block runs on rank 0 alone.
+            if world == 1:
+              try:
                 pn.set_mlp_mode("fp32")
                 for i in range(2):
                     step_resident(i)
                 ms32 = time_steps(step_resident, 3, 1)
                 line["fp32_mode"] = {"value": RAYS_PER_RANK * 3 / (ms32 / 1e3), "unit": "rays/s", "ms_per_step": ms32 / 3,
                                      "what": "same step with the fp32 FFMA NeRFSmall kernels and unfused hash kernels"}
-            except Exception as ex:
+              except Exception as ex:
                 line["fp32_mode"] = {"error": repr(ex)}
-            finally:
+              finally:
                 pn.set_mlp_mode(MLP_MODE)
         # ---- config 2: full 800x800 test-view render, finest_res 1024 -----------------------------------
         try:
@@ -374,10 +379,31 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "ms_per_step": msc,
                                     "sample": "1024 rays/step of the same workload (64+128 samples, T=2^19), full "
                                               "train step by the oracle, 1 warm-up + 3 timed steps"}
-        print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+    return line if rank == 0 else None
+
+
+class StdoutToStderr:
+    """Everything written to fd 1 while active goes to stderr (NCCL prints its version banner on stdout), so
+    that the ONE JSON line is the only thing this program ever writes to stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(1, (json.dumps(line) + "\n").encode())
 
 
 def main():
@@ -389,10 +415,10 @@ def main():
     ap.add_argument("--no-baselines", action="store_true", help="skip the CPU / eager-GPU baseline legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with StdoutToStderr() as guard:
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if line is not None:
+        emit(line)
 
 
 if __name__ == "__main__":
