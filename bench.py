@@ -48,11 +48,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -62,7 +69,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -75,7 +82,11 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.15]
+        window = "timed region"
+        if not inside:      # region shorter than the sampling period: fall back to the samples taken under load (warm-up)
+            inside, window = [r for t, r in self.rows], "warm-up + timed region"
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[2:6]):
@@ -85,7 +96,8 @@ class ClockSampler:
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def dist_setup(n):
@@ -210,13 +222,16 @@ def run_ours(args):
         loss, _ = tr.step(r.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
         losses.append(loss.item())
 
-    for i in range(args.warmup):
-        step_e2e(i)
     with ClockSampler(local) as clk:
+        for i in range(args.warmup):
+            step_e2e(i)
+        torch.cuda.synchronize()
+        clk.mark_start()
         l0 = _lib.launch_count()
         ms = time_steps(step_resident, args.steps, world)
         launches = _lib.launch_count() - l0
         ms_e2e = time_steps(step_e2e, args.steps, world)
+        clk.mark_end()
     rays_total = RAYS_PER_RANK * world * args.steps
     value = rays_total / (ms / 1e3)
     e2e = rays_total / (ms_e2e / 1e3)
@@ -409,7 +424,7 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-baselines", action="store_true", help="skip the CPU / eager-GPU baseline legs")
