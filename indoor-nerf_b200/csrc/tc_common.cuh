@@ -88,6 +88,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 2 consecutive columns (one hash level's two feature gradients)
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float &a, float &b) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+  a = __uint_as_float(r0);
+  b = __uint_as_float(r1);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- MMA ---------------------------------------------------------------------------------------------------
