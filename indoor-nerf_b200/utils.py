@@ -14,8 +14,9 @@ PRIMES = (1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 21652197
 
 
 def hash(coords, log2_hashmap_size):
-    """utils.py:13-24.  CUDA tensors with <= 3 coordinates go through the kernel; anything else (CPU
-    tensors during set-up, >3-D coordinates) uses the defining integer formula."""
+    """utils.py:13-24.  CUDA tensors with <= 3 coordinates (every call on the training path: the TV loss,
+    loss.py:29) go through the kernel.  The defining integer formula below is only reached by host-side set-up
+    code and unit tests holding CPU tensors, or by the reference's unused 4..7-D case."""
     if coords.is_cuda and coords.shape[-1] <= 3:
         return ops.hash_coords(coords, log2_hashmap_size)
     acc = torch.zeros_like(coords)[..., 0]
