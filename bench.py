@@ -109,7 +109,7 @@ def dist_setup(n):
         import datetime
         # a short collective timeout: a rank-divergent code path must fail in minutes, not hold N GPUs for the
         # default 10 minutes
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=150))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
         return dist.get_rank(), world, local
     return 0, 1, 0
 
