@@ -222,11 +222,13 @@ __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, con
   } else {
     float xv[3] = {0.f, 0.f, 0.f};
     if (valid) { xv[0] = __ldg(F->pts + 3 * (base + p)); xv[1] = __ldg(F->pts + 3 * (base + p) + 1); xv[2] = __ldg(F->pts + 3 * (base + p) + 2); }
-    float f[16];
-#pragma unroll
+    // rolled (x2) loop over this thread's 8 levels, each level's two features stored straight into the operand tile
+    // (4 bytes at chunk l/4, slot l%4): keeps one level's state live instead of 16 features + 8 levels of code
+#pragma unroll 2
     for (int i = 0; i < 8; ++i) {
       const int l = half * 8 + i;
-      if (l < F->G.n_levels) {
+      float f0 = 0.f, f1 = 0.f;
+      if (l < F->G.n_levels && valid) {
         Cell c;
         point_cell<false>(F->G, l, xv, c);
         const float2 *__restrict__ tab = F->T.t[l];
@@ -245,21 +247,17 @@ __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, con
             }
           }
         }
-        f[2 * i] = trilerp_fast(e0, c.w);
-        f[2 * i + 1] = trilerp_fast(e1, c.w);
-      } else {
-        f[2 * i] = 0.f; f[2 * i + 1] = 0.f;
+        f0 = trilerp_fast(e0, c.w);
+        f1 = trilerp_fast(e1, c.w);
       }
+      *reinterpret_cast<uint32_t *>(sm + TS::A0 + chunk_off(p, l >> 2, 4) + (l & 3) * 4) = pack_bf16(f0, f1);
     }
-    if (!valid) {
+    if (F->featb) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = 0.f;
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const uint32_t off = chunk_off(p, half * 2 + c, 4);
-      st_chunk(sm + TS::A0, off, f + 8 * c);
-      if (F->featb) F->featb[tile * 512 + (off >> 4)] = *reinterpret_cast<const uint4 *>(sm + TS::A0 + off);
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t off = chunk_off(p, half * 2 + c, 4);
+        F->featb[tile * 512 + (off >> 4)] = *reinterpret_cast<const uint4 *>(sm + TS::A0 + off);
+      }
     }
     if (half == 0 && valid && F->keep_out) F->keep_out[base + p] = point_keep(F->G, xv) ? 1 : 0;
   }
@@ -750,7 +748,12 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
   const int smem = A.normals ? TS::FWD_END : TS::NH;
   // the fused variant carries the hash-gather state: at 4 CTAs/SM (64 registers) it spills and measured 25 %
   // slower than at 3 CTAs/SM (76 registers), so it stays at 3
-  const int per_sm = (A.normals || fused) ? 3 : 4;       // x 128 TMEM columns each
+  static int fused_ctas = -1;
+  if (fused_ctas < 0) {                                  // tuning knob
+    const char *e = getenv("PN_FWD_CTAS");
+    fused_ctas = (e && atoi(e) == 4) ? 4 : 3;
+  }
+  const int per_sm = A.normals ? 3 : (fused ? fused_ctas : 4);   // x 128 TMEM columns each
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -758,13 +761,15 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
     cudaError_t e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<4, SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<4, SRC_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_fwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int blocks = (int)(tiles < cap ? tiles : cap);
-  if (fused) mlp_tc_fwd_kernel<3, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  if (fused && per_sm == 4) mlp_tc_fwd_kernel<4, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  else if (fused) mlp_tc_fwd_kernel<3, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   else if (A.normals) mlp_tc_fwd_kernel<3, SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   else mlp_tc_fwd_kernel<4, SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   count_launch();
