@@ -69,6 +69,9 @@ def hash_encode_fwd(grid, tables, x, qparams=None):
     P = x.shape[0]
     feat = torch.empty((P, 2 * grid.n_levels), dtype=torch.float32, device=x.device)
     keep = torch.empty((P,), dtype=torch.bool, device=x.device)
+    if P == 0:
+        _guard(x)
+        return feat, keep
     with _guard(x):
         call("pn_hash_encode_fwd", ctypes.byref(grid), _ptr_array(tables), dptr(qparams, allow_none=True),
              dptr(x), P, dptr(feat), dptr(keep, torch.bool), stream())
@@ -79,6 +82,8 @@ def hash_encode_bwd(grid, dtables, x, dfeat):
     """Accumulate the dense table gradients into dtables (list of [T,2], caller-zeroed)."""
     x, dfeat = fcontig(x), fcontig(dfeat)
     _check_tables(grid, dtables)
+    if x.shape[0] == 0:
+        return
     with _guard(x):
         call("pn_hash_encode_bwd", ctypes.byref(grid), _ptr_array(dtables), dptr(x), dptr(dfeat), x.shape[0],
              stream())
@@ -87,6 +92,8 @@ def hash_encode_bwd(grid, dtables, x, dfeat):
 def hash_indices(grid, x):
     x = fcontig(x)
     idx = torch.empty((x.shape[0], grid.n_levels, 8), dtype=torch.int32, device=x.device)
+    if x.shape[0] == 0:
+        return idx
     with _guard(x):
         call("pn_hash_indices", ctypes.byref(grid), dptr(x), x.shape[0], dptr(idx, torch.int32), stream())
     return idx
@@ -97,6 +104,8 @@ def hash_coords(coords, log2_hashmap_size):
     c = coords.to(torch.int64).contiguous()
     out = torch.empty(c.shape[:-1], dtype=torch.int64, device=c.device)
     n = out.numel()
+    if n == 0:
+        return out
     with _guard(c):
         call("pn_hash_coords", dptr(c, torch.int64), n, c.shape[-1], int(log2_hashmap_size), dptr(out, torch.int64),
              stream())
@@ -231,6 +240,8 @@ def sh_encode(dirs):
     """hash_encoding.py:153-191, degree 4."""
     d = fcontig(dirs.reshape(-1, 3))
     out = torch.empty((d.shape[0], 16), dtype=torch.float32, device=d.device)
+    if d.shape[0] == 0:
+        return out.reshape(*dirs.shape[:-1], 16)
     with _guard(d):
         call("pn_sh_encode", dptr(d), d.shape[0], dptr(out), stream())
     return out.reshape(*dirs.shape[:-1], 16)
@@ -274,6 +285,9 @@ def mlp_fwd(w, feat, sh=None, dirs=None, samples_per_ray=1, act_q=None, keep=Non
     out[P, 4|7].   Reference: run_nerf_helpers.py:265-306 (+ run_nerf.py:59-66 when dirs/keep given)."""
     C = 7 if w.get("n0w") is not None else 4
     out = torch.empty((feat.shape[0], C), dtype=torch.float32, device=feat.device)
+    if feat.shape[0] == 0:
+        _guard(feat)
+        return out
     with _guard(feat):
         ws, inp = _weights_struct(w), _mlp_input(feat, sh, dirs, samples_per_ray, act_q, keep)
         call("pn_mlp_fwd_bf16" if (mode or _MLP_MODE) == "bf16" else "pn_mlp_fwd", ctypes.byref(ws), ctypes.byref(inp),
@@ -288,6 +302,8 @@ def mlp_bwd(w, feat, dout, sh=None, dirs=None, samples_per_ray=1, act_q=None, ke
     dfeat = torch.empty((P, 32), dtype=torch.float32, device=feat.device)
     dsh = torch.empty((P, 16), dtype=torch.float32, device=feat.device) if (want_dsh and sh is not None) else None
     dw = {k: torch.zeros_like(w[k]) for k in _MLP_KEYS if w.get(k) is not None}
+    if P == 0:
+        return dfeat, dsh, dw
     with _guard(feat):
         ws, inp = _weights_struct(w), _mlp_input(feat, sh, dirs, samples_per_ray, act_q, keep)
         gs = _weights_struct(dw)
@@ -334,7 +350,7 @@ class FieldFn(torch.autograd.Function):
         dirs = fcontig(viewdirs)
         w = {k: fcontig(t.detach()) for k, t in zip(keys, weights)}
         ctx.mode = _MLP_MODE
-        ctx.fused = ctx.mode == "bf16" and grid.n_levels == 16
+        ctx.fused = ctx.mode == "bf16" and grid.n_levels == 16 and pts.shape[0] > 0
         if ctx.fused:
             # one kernel: hash encode -> SH -> NeRFSmall (tcgen05) -> keep mask; features saved as bf16 operand tiles
             P = pts.shape[0]
@@ -401,7 +417,8 @@ class CompositeFn(torch.autograd.Function):
         f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         rgb, disp, acc, wts, depth, sp = f(N, 3), f(N), f(N), f(N, S), f(N), f(N)
         normal = f(N, 3) if C == 7 else None
-        with _guard(raw):
+        if N > 0:
+          with _guard(raw):
             call("pn_composite_fwd", dptr(raw), C, dptr(z), dptr(rays_d), dptr(noise, allow_none=True), N, S,
                  int(bool(white)), dptr(rgb), dptr(disp), dptr(acc), dptr(wts), dptr(depth), dptr(sp),
                  dptr(normal, allow_none=True), stream())
@@ -419,7 +436,8 @@ class CompositeFn(torch.autograd.Function):
         draw = torch.empty_like(raw)
         c = lambda t: fcontig(t) if t is not None else None
         d_rgb, d_disp, d_acc, d_wts, d_depth, d_sp, d_normal = map(c, (d_rgb, d_disp, d_acc, d_wts, d_depth, d_sp, d_normal))
-        with _guard(raw):
+        if N > 0:
+          with _guard(raw):
             call("pn_composite_bwd", dptr(raw), C, dptr(z), dptr(rays_d), dptr(noise, allow_none=True), N, S,
                  int(ctx.white), *[dptr(t, allow_none=True) for t in (d_rgb, d_disp, d_acc, d_wts, d_depth, d_sp, d_normal)],
                  dptr(draw), stream())
@@ -451,7 +469,8 @@ def sample_pdf(bins, weights, u, return_inds=False, return_cdf=False):
     samples = torch.empty((N, M), dtype=torch.float32, device=bins.device)
     inds = torch.empty((N, M), dtype=torch.int32, device=bins.device) if return_inds else None
     cdf = torch.empty((N, nb), dtype=torch.float32, device=bins.device) if return_cdf else None
-    with _guard(bins):
+    if N > 0:
+      with _guard(bins):
         call("pn_sample_pdf", dptr(bins), ctypes.c_void_p(weights.data_ptr()), weights.stride(0), dptr(u), us, N, nb, M,
              dptr(samples), dptr(inds, torch.int32, allow_none=True), dptr(cdf, allow_none=True), stream())
     out = (samples,)
@@ -469,7 +488,8 @@ def sample_from_cdf(cdf, bins, u):
     u, us = _u_arg(u, N, M)
     samples = torch.empty((N, M), dtype=torch.float32, device=bins.device)
     inds = torch.empty((N, M), dtype=torch.int32, device=bins.device)
-    with _guard(bins):
+    if N > 0:
+      with _guard(bins):
         call("pn_sample_from_cdf", dptr(cdf), dptr(bins), dptr(u), us, N, nb, M, dptr(samples),
              dptr(inds, torch.int32), stream())
     return samples, inds
@@ -480,7 +500,8 @@ def sort_merge(a, b):
     a, b = fcontig(a.detach()), fcontig(b.detach())
     N = a.shape[0]
     out = torch.empty((N, a.shape[1] + b.shape[1]), dtype=torch.float32, device=a.device)
-    with _guard(a):
+    if N > 0:
+      with _guard(a):
         call("pn_sort_merge", dptr(a), a.shape[1], dptr(b), b.shape[1], N, dptr(out), stream())
     return out
 
@@ -502,7 +523,8 @@ def ndc_rays(H, W, focal, near, rays_o, rays_d):
     shape = rays_o.shape
     o, d = fcontig(rays_o.reshape(-1, 3)), fcontig(rays_d.reshape(-1, 3))
     oo, od = torch.empty_like(o), torch.empty_like(d)
-    with _guard(o):
+    if o.shape[0] > 0:
+      with _guard(o):
         call("pn_ndc_rays", int(H), int(W), float(focal), float(near), dptr(o), dptr(d), o.shape[0], dptr(oo), dptr(od),
              stream())
     return oo.reshape(shape), od.reshape(shape)
@@ -520,7 +542,8 @@ def make_points(rays_o, rays_d, z):
 
     o, d = rows(rays_o), rows(rays_d)
     pts = torch.empty((N, S, 3), dtype=torch.float32, device=z.device)
-    with _guard(z):
+    if N > 0:
+      with _guard(z):
         call("pn_make_points", ctypes.c_void_p(o.data_ptr()), o.stride(0), ctypes.c_void_p(d.data_ptr()), d.stride(0),
              dptr(z), N, S, dptr(pts), stream())
     return pts
@@ -535,7 +558,8 @@ def coarse_z(near, far, t_vals, t_rand=None, lindisp=False):
     t_vals = fcontig(t_vals)
     t_rand = fcontig(t_rand) if t_rand is not None else None
     z = torch.empty((N, S), dtype=torch.float32, device=t_vals.device)
-    with _guard(z):
+    if N > 0:
+      with _guard(z):
         call("pn_coarse_z", ctypes.c_void_p(near.data_ptr()), ctypes.c_void_p(far.data_ptr()), near.stride(0),
              dptr(t_vals), dptr(t_rand, allow_none=True), N, S, int(bool(lindisp)), dptr(z), stream())
     return z

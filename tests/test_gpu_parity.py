@@ -666,3 +666,55 @@ def test_config_llff_ndc_quantized(pn):
         close(ret[k], ref[k], 5e-5, k)
     for k in ["rgb_map", "acc_map", "raw"]:
         close_l2(ret[k], ref[k], 2e-3, k)
+
+
+def test_empty_and_ragged_inputs(pn):
+    """Edge cases: zero rays / zero points everywhere on the path, and sample counts that are not multiples of
+    the warp or tile size (S = 50, 3 rays; 1 ray) — against the oracle."""
+    box = (torch.tensor([-3.0] * 3), torch.tensor([3.0] * 3))
+    emb = pn.HashEmbedder(box, log2_hashmap_size=12).cuda().train()
+    with torch.no_grad():
+        emb.table_storage.uniform_(-0.3, 0.3)
+    w = mlp_weights(71)
+    net = mlp_from(pn, w)
+    sh = pn.SHEncoder()
+    query = lambda inputs, viewdirs, fn: pn.run_network(inputs, viewdirs, fn, embed_fn=emb, embeddirs_fn=sh)
+    # --- empty ---
+    feat, keep = emb(torch.zeros(0, 3, device="cuda"))
+    assert feat.shape == (0, 32) and keep.shape == (0,)
+    assert net(torch.zeros(0, 48, device="cuda")).shape == (0, 4)
+    assert sh(torch.zeros(0, 3, device="cuda")).shape == (0, 16)
+    for mode in ("fp32", "bf16"):
+        pn.set_mlp_mode(mode)
+        try:
+            ret = pn.render_rays(torch.zeros(0, 11, device="cuda"), net, query, 64, embed_fn=emb, retraw=True, perturb=1.0,
+                                 N_importance=128, network_fine=net, white_bkgd=True)
+            assert ret["rgb_map"].shape == (0, 3) and ret["raw"].shape == (0, 192, 4) and ret["pts"].shape == (0, 192, 3)
+            (ret["rgb_map"].sum() + ret["rgb0"].sum()).backward()
+        finally:
+            pn.set_mlp_mode("fp32")
+    # --- ragged: S = 50 coarse + 30 fine, N = 3 and N = 1 ---
+    tabs = [e.weight.detach() for e in emb.embeddings]
+    res = O.level_resolutions(16, 512, device="cuda")
+    embed = lambda x: O.hash_embed(x, box[0].cuda(), box[1].cuda(), tabs, res, 12)
+    wd = {k: v.cuda() for k, v in w.items()}
+    q = lambda pts, vd: O.run_network(pts, vd, embed, lambda x: O.nerf_small(x, wd))
+    for N in (3, 1):
+        rs = np.random.RandomState(N)
+        o = (rs.randn(N, 3) * 0.2 + np.array([0, 0, 4.0])).astype(np.float32)
+        d = (rs.randn(N, 3) * 0.8 - o).astype(np.float32)
+        d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        rays = cu(np.concatenate([o, d, np.full((N, 1), 2.0, np.float32), np.full((N, 1), 6.0, np.float32), d], -1))
+        t_rand, u = torch.rand(N, 50, device="cuda"), torch.rand(N, 30, device="cuda")
+        ref = O.render_rays(rays, q, q, 50, 30, t_rand=t_rand, u=u, white_bkgd=True)
+        for mode, tol in (("fp32", 5e-5), ("bf16", 2e-2)):
+            pn.set_mlp_mode(mode)
+            try:
+                with _Rng([t_rand, u], []):
+                    ret = pn.render_rays(rays, net, query, 50, embed_fn=emb, retraw=True, perturb=1.0, N_importance=30,
+                                         network_fine=net, white_bkgd=True)
+            finally:
+                pn.set_mlp_mode("fp32")
+            assert ret["raw"].shape == (N, 80, 4)
+            for k in ["rgb0", "acc0"]:
+                close(ret[k], ref[k], tol, "%s N=%d %s" % (k, N, mode))
