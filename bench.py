@@ -190,6 +190,20 @@ def workload_config(n):
                          "through; the 64 MiB table set is L2-resident by design"}
 
 
+def fp32_mode_leg(pn, step_resident):
+    try:
+        pn.set_mlp_mode("fp32")
+        for i in range(2):
+            step_resident(i)
+        ms32 = time_steps(step_resident, 3, 1)
+        return {"value": RAYS_PER_RANK * 3 / (ms32 / 1e3), "unit": "rays/s", "ms_per_step": ms32 / 3,
+                "what": "same step with the fp32 FFMA NeRFSmall kernels and unfused hash kernels"}
+    except Exception as ex:
+        return {"error": repr(ex)}
+    finally:
+        pn.set_mlp_mode(MLP_MODE)
+
+
 def run_ours(args):
     import indoor_nerf_b200 as pn
     from indoor_nerf_b200 import _lib, model as pmodel, ops, synthetic
@@ -334,17 +348,7 @@ def run_ours(args):
             # the same training step in the fp32 (FFMA, 1e-5 parity) mode.  Single-GPU runs only: Trainer.step
             # all-reduces, and this block runs on rank 0 alone.
             if world == 1:
-              try:
-                pn.set_mlp_mode("fp32")
-                for i in range(2):
-                    step_resident(i)
-                ms32 = time_steps(step_resident, 3, 1)
-                line["fp32_mode"] = {"value": RAYS_PER_RANK * 3 / (ms32 / 1e3), "unit": "rays/s", "ms_per_step": ms32 / 3,
-                                     "what": "same step with the fp32 FFMA NeRFSmall kernels and unfused hash kernels"}
-              except Exception as ex:
-                line["fp32_mode"] = {"error": repr(ex)}
-              finally:
-                pn.set_mlp_mode(MLP_MODE)
+                line["fp32_mode"] = fp32_mode_leg(pn, step_resident)
         # ---- config 2: full 800x800 test-view render, finest_res 1024 -----------------------------------
         try:
             scene2 = synthetic.blender_scene(800, 800, n_views=8)

@@ -99,11 +99,17 @@ def render_sharded(render_fn, H, W, rays_o, rays_d, group=None, gather=True, **k
     rgb, depth, acc = out[0], out[1], out[2]
     if world == 1 or not gather:
         return rgb, depth, acc
+    rows = [pixel_rows(H, k, world) for k in range(world)]
+    equal = len({b - a for a, b in rows}) == 1
     res = []
     for t in (rgb, depth, acc):
-        rows = [pixel_rows(H, k, world) for k in range(world)]
+        t = t.contiguous()
         parts = [torch.empty((b - a,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for a, b in rows]
-        dist.all_gather(parts, t.contiguous(), group=group) if len({b - a for a, b in rows}) == 1 else \
-            [dist.broadcast(parts[k] if k != r else parts[k].copy_(t), src=k, group=group) for k in range(world)]
+        if equal:
+            dist.all_gather(parts, t, group=group)
+        else:                                   # ragged row blocks: one broadcast per owner
+            parts[r].copy_(t)
+            for k in range(world):
+                dist.broadcast(parts[k], src=k, group=group)
         res.append(torch.cat(parts, 0))
     return tuple(res)
