@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 6
+#define PN_ABI_VERSION 7
 #define PN_MAX_LEVELS 16
 
 #define PN_EINVAL (-1)   /* bad argument */
@@ -255,6 +255,49 @@ int pn_tv_loss_bwd(const float *const *tables, float *const *dtables, int n_leve
 int pn_radam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
                   float beta2, float eps, float weight_decay_times_lr, float step_size_times_lr, int mode,
                   pn_stream_t stream);
+
+/* ---- data formats either side of the path -------------------------------------- */
+
+/* A training batch straight from (image, pixel) ids: replaces the precomputed rays_rgb tensor of the
+ * use_batching branch (run_nerf.py:896-920 builds [N*H*W, ro+rd+rgb, 3] fp32 = 36 B/ray; :962-966 slices it)
+ * and the full-image get_rays + gather of the no_batching branch (run_nerf.py:976-1004).
+ *   ids          device int64 [n_rays]; ids[b] = (slot*H + j)*W + i, slot = position of the image in i_train
+ *                (the row order of rays_rgb before shuffling), (j, i) = pixel row / column.
+ *   K            host double[9], row-major intrinsics (fx = K[0], cx = K[2], fy = K[4], cy = K[5]).
+ *   poses        device fp32, camera-to-world [3,4] row-major at poses + image*pose_stride (pose_stride = 12 for
+ *                [N,3,4], 16 for [N,4,4]).
+ *   image_index  device int32 [n_slots] mapping slot -> image row, or NULL for identity.
+ *   images       device [n_images, H, W, 3], fp32 (image_dtype 0) or uint8 (image_dtype 1, converted as
+ *                load_blender.py:62 does: float32(u8 / 255.0) with the division in double); NULL with target NULL.
+ *   f64_dirs     1: ray directions in the arithmetic of get_rays_np as train() calls it (run_nerf_helpers.py:323-330
+ *                with a float64 K: float64 ops, rounded to fp32 by run_nerf.py:905); 0: the fp32 arithmetic of
+ *                get_rays (run_nerf_helpers.py:311-320).  Both bit-exact.
+ *   batch_rays   device fp32 [2, n_rays, 3] (origins, then directions); target device fp32 [n_rays, 3]. */
+int pn_ray_bank_batch(const int64_t *ids, int64_t n_rays, int height, int width, const double *K,
+                      const float *poses, int64_t pose_stride, const int32_t *image_index, const void *images,
+                      int image_dtype, int f64_dirs, float *batch_rays, float *target, pn_stream_t stream);
+
+/* *sum += sum_k (a[k]-b[k])^2 (differences and squares rounded in fp32 as np.square(rgb - gt) does, accumulated in
+ * fp64; sum is a caller-zeroed DEVICE double) — the numerator of render_path's PSNR (run_nerf.py:186) and
+ * ComprehensiveEvaluator.compute_metrics (evaluation_utils.py:24-25) without the image leaving the GPU. */
+int pn_image_sqerr(const float *a, const float *b, int64_t n, double *sum, pn_stream_t stream);
+
+/* *sum += sum over interior pixels and channels of the SSIM map of two [H,W,C] fp32 images, as
+ * skimage.metrics.structural_similarity(channel_axis=2, data_range=...) computes it with its defaults
+ * (evaluation_utils.py:33; scikit-image 0.25.2: 7x7 uniform window, sample covariance, K1=0.01, K2=0.03,
+ * mean over the map cropped by 3 pixels per side).  mean SSIM = *sum / ((H-6)*(W-6)*C). */
+int pn_image_ssim(const float *a, const float *b, int height, int width, int channels, double data_range,
+                  double *sum, pn_stream_t stream);
+
+/* out[k] = uint8(255*clip(x[k],0,1))  — to8b (run_nerf_helpers.py:13), truncating like numpy's astype. */
+int pn_to8b(const float *x, int64_t n, uint8_t *out, pn_stream_t stream);
+
+/* Integer codes of LearnedBitwidthQuantizer's eval form (quantization.py:157-187), bit-packed at the learned
+ * width: code = clamp(round(x/(scale+1e-8) + zp), qmin, qmax) - qmin, `bits` bits per value, 32 values per
+ * `bits` little-endian 32-bit words.  qrow: device [PN_QROW] (the eval-form row).  n % 32 == 0, 1 <= bits <= 24.
+ * pn_quant_unpack writes (code + qmin - zp) * scale, bit-identical to the quantiser's eval output on x. */
+int pn_quant_pack(const float *x, int64_t n, const float *qrow, int bits, uint32_t *words, pn_stream_t stream);
+int pn_quant_unpack(const uint32_t *words, int64_t n, const float *qrow, int bits, float *x, pn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,9 @@ from .hash_encoding import HashEmbedder, SHEncoder  # noqa: F401
 from .quantization import FakeQuantizer, LearnedBitwidthQuantizer, PassthroughQuantizer, calculate_fqr  # noqa: F401
 from .run_nerf_helpers import (NeRFSmall, get_embedder, get_rays, get_rays_np, img2mse, mse2psnr, ndc_rays,  # noqa: F401
                                sample_pdf, to8b)
-from .render import batchify, batchify_rays, patch, raw2outputs, render, render_rays, run_network  # noqa: F401
+from .render import batchify, batchify_rays, patch, raw2outputs, render, render_path, render_rays, run_network  # noqa: F401
+from .ray_bank import RayBank  # noqa: F401
+from .evaluation_utils import ComprehensiveEvaluator  # noqa: F401
+from . import quant_export  # noqa: F401
 
 __version__ = "0.1.0"

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpocketnerf.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LEVELS = 16
 QROW = 8
 
@@ -66,6 +66,12 @@ _SIGNATURES = {
     "pn_ndc_rays": [_I, _I, ctypes.c_double, ctypes.c_double, _P, _P, _L, _P, _P, _P],
     "pn_make_points": [_P, _L, _P, _L, _P, _L, _I, _P, _P],
     "pn_coarse_z": [_P, _P, _L, _P, _P, _L, _I, _I, _P, _P],
+    "pn_ray_bank_batch": [_P, _L, _I, _I, _P, _P, _L, _P, _P, _I, _I, _P, _P, _P],
+    "pn_image_sqerr": [_P, _P, _L, _P, _P],
+    "pn_image_ssim": [_P, _P, _I, _I, _I, ctypes.c_double, _P, _P],
+    "pn_to8b": [_P, _L, _P, _P],
+    "pn_quant_pack": [_P, _L, _P, _I, _P, _P],
+    "pn_quant_unpack": [_P, _L, _P, _I, _P, _P],
 }
 # entry points added by later kernels (fused field, tensor-core MLP, optimizer); bound when exported
 _OPTIONAL = {}

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -ffp-contract=off --expt-relaxed-constexpr"
 SRCS="api.cu hash_encode.cu composite.cu sample.cu rays.cu mlp_fp32.cu"
-for extra in mlp_tc.cu fused.cu optim.cu; do [ -f "$extra" ] && SRCS="$SRCS $extra"; done
+for extra in mlp_tc.cu fused.cu optim.cu dataio.cu; do [ -f "$extra" ] && SRCS="$SRCS $extra"; done
 mkdir -p build
 objs=""
 pids=""

@@ -563,3 +563,92 @@ def coarse_z(near, far, t_vals, t_rand=None, lindisp=False):
         call("pn_coarse_z", ctypes.c_void_p(near.data_ptr()), ctypes.c_void_p(far.data_ptr()), near.stride(0),
              dptr(t_vals), dptr(t_rand, allow_none=True), N, S, int(bool(lindisp)), dptr(z), stream())
     return z
+
+
+# ---------------------------------------------------------------------------------------------------
+# data formats either side of the path
+# ---------------------------------------------------------------------------------------------------
+def ray_bank_batch(ids, H, W, K, poses, image_index=None, images=None, f64_dirs=True):
+    """batch_rays [2,B,3] (and target_s [B,3] when images is given) for ray ids (slot*H + j)*W + i.
+    poses: CUDA fp32 [N,3,4] or [N,4,4]; images: CUDA fp32 or uint8 [N,H,W,3].  f64_dirs=True reproduces the
+    precomputed bank of run_nerf.py:899-905 (get_rays_np with a float64 K), False the get_rays of :981."""
+    if ids.dtype != torch.int64:
+        ids = ids.to(torch.int64)
+    ids = ids.contiguous()
+    B = ids.shape[0]
+    poses = fcontig(poses)
+    if poses.dim() != 3 or tuple(poses.shape[1:]) not in ((3, 4), (4, 4)):
+        raise _lib.PocketNerfError("poses must be [N,3,4] or [N,4,4], got %s" % (tuple(poses.shape),))
+    Kd = (ctypes.c_double * 9)(*[float(K[i][j]) for i in range(3) for j in range(3)])
+    rays = torch.empty((2, B, 3), dtype=torch.float32, device=ids.device)
+    target, img_ptr, img_dt = None, None, 0
+    if images is not None:
+        if images.dtype not in (torch.float32, torch.uint8) or tuple(images.shape[1:]) != (H, W, 3):
+            raise _lib.PocketNerfError("images must be fp32 or uint8 [N,%d,%d,3], got %s %s" % (H, W, images.dtype, tuple(images.shape)))
+        img_dt = 1 if images.dtype == torch.uint8 else 0
+        img_ptr = dptr(images, images.dtype)
+        target = torch.empty((B, 3), dtype=torch.float32, device=ids.device)
+    if B > 0:
+        with _guard(ids):
+            call("pn_ray_bank_batch", dptr(ids, torch.int64), B, int(H), int(W), Kd, dptr(poses),
+                 poses.shape[1] * poses.shape[2], dptr(image_index, torch.int32, allow_none=True), img_ptr, img_dt,
+                 int(bool(f64_dirs)), dptr(rays), dptr(target, allow_none=True), stream())
+    else:
+        _guard(ids)
+    return (rays, target) if images is not None else rays
+
+
+def image_sqerr(a, b, out=None):
+    """Device double scalar: sum((a-b)^2) — accumulated into `out` when given (caller-zeroed)."""
+    a, b = fcontig(a), fcontig(b)
+    if a.shape != b.shape:
+        raise _lib.PocketNerfError("shape mismatch %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+    s = out if out is not None else torch.zeros((), dtype=torch.float64, device=a.device)
+    if a.numel() > 0:
+        with _guard(a):
+            call("pn_image_sqerr", dptr(a), dptr(b), a.numel(), dptr(s, torch.float64), stream())
+    else:
+        _guard(a)
+    return s
+
+
+def image_ssim(a, b, data_range=1.0):
+    """Mean SSIM of two [H,W,C] images as a device double scalar (scikit-image defaults, evaluation_utils.py:33)."""
+    a, b = fcontig(a), fcontig(b)
+    if a.shape != b.shape or a.dim() != 3:
+        raise _lib.PocketNerfError("expected two [H,W,C] images, got %s and %s" % (tuple(a.shape), tuple(b.shape)))
+    H, W, C = a.shape
+    s = torch.zeros((), dtype=torch.float64, device=a.device)
+    with _guard(a):
+        call("pn_image_ssim", dptr(a), dptr(b), H, W, C, float(data_range), dptr(s, torch.float64), stream())
+    return s / float((H - 6) * (W - 6) * C)
+
+
+def to8b(x):
+    """uint8 image (255*clip(x,0,1)).astype(uint8) on the device (run_nerf_helpers.py:13)."""
+    x = fcontig(x)
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    if x.numel() > 0:
+        with _guard(x):
+            call("pn_to8b", dptr(x), x.numel(), dptr(out, torch.uint8), stream())
+    else:
+        _guard(x)
+    return out
+
+
+def quant_pack(x, qrow, bits):
+    """int32 words [n*bits/32]: the eval-form integer codes of a LearnedBitwidthQuantizer, bit-packed."""
+    x = fcontig(x).reshape(-1)
+    n = x.numel()
+    words = torch.empty((n * int(bits) // 32,), dtype=torch.int32, device=x.device)
+    with _guard(x):
+        call("pn_quant_pack", dptr(x), n, dptr(fcontig(qrow)), int(bits), dptr(words, torch.int32), stream())
+    return words
+
+
+def quant_unpack(words, n, qrow, bits):
+    """fp32 [n]: (code + qmin - zp) * scale — what the quantiser's eval forward returns for the packed tensor."""
+    x = torch.empty((n,), dtype=torch.float32, device=words.device)
+    with _guard(words):
+        call("pn_quant_unpack", dptr(words.contiguous(), torch.int32), n, dptr(fcontig(qrow)), int(bits), dptr(x), stream())
+    return x

@@ -1,5 +1,5 @@
 """Drop-in for the renderer functions that live inside the reference's run_nerf.py: batchify,
-run_network, batchify_rays, render, raw2outputs, render_rays (run_nerf.py:43-151, 347-549).
+run_network, batchify_rays, render, render_path, raw2outputs, render_rays (run_nerf.py:43-215, 347-549).
 
 Same signatures, same return structure, same use of torch's global RNG; the arithmetic runs in the
 sm_100a kernels (ops.py).  ``patch(run_nerf_module)`` installs them into an imported reference driver.
@@ -175,9 +175,90 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
 
 
+def _write_png(path, img8):
+    """Minimal PNG writer (8-bit gray [H,W] or RGB [H,W,3]); the reference saves matplotlib figures
+    (run_nerf.py:190-205), which is plotting and out of scope — the pixels are what matters here."""
+    import struct
+    import zlib
+    img8 = np.ascontiguousarray(img8)
+    h, w = img8.shape[:2]
+    color = 2 if img8.ndim == 3 else 0
+    raw = b"".join(b"\x00" + img8[r].tobytes() for r in range(h))
+
+    def chunk(tag, data):
+        c = struct.pack(">I", len(data)) + tag + data
+        return c + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, color, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0, group=None):
+    """run_nerf.py:154-215 -> (rgbs [n,H,W,3], depths [n,H,W]) as numpy arrays, depths normalised by near/far.
+
+    Differences in HOW, not WHAT: the squared error of every frame is reduced on the device (pn_image_sqerr) and
+    all PSNRs are read back with one transfer at the end instead of a host round trip per frame; frames are
+    copied to pinned host memory asynchronously; with a process group every frame is rendered pixel-sharded
+    (row blocks, no collective on the data path, one all-gather of the finished frame).  Saved images are plain
+    PNGs of to8b(rgb) and of the normalised depth."""
+    import os
+    import pickle
+    from . import parallel
+
+    H, W, focal = hwf
+    near, far = render_kwargs["near"], render_kwargs["far"]
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    H, W = int(H), int(W)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = len(render_poses)
+    world = parallel.world_size(group)
+    pin = dict(pin_memory=True)
+    rgbs = torch.empty((n, H, W, 3), dtype=torch.float32, **pin)
+    depths = torch.empty((n, H, W), dtype=torch.float32, **pin)
+    want_psnr = gt_imgs is not None and render_factor == 0
+    sq = torch.zeros(n, dtype=torch.float64, device=dev) if want_psnr else None
+    rgb8s = []
+    with torch.no_grad():
+        for i, c2w in enumerate(render_poses):
+            c2w = torch.as_tensor(c2w)[:3, :4]
+            if world > 1:
+                ro, rd = get_rays(H, W, K, c2w)
+                kw = {k: v for k, v in render_kwargs.items()}
+                rgb, depth, _ = parallel.render_sharded(lambda h, w, **a: render(h, w, K, chunk=chunk, **a), H, W, ro, rd,
+                                                        group=group, gather=True, **kw)
+            else:
+                rgb, depth, _, _ = render(H, W, K, chunk=chunk, c2w=c2w, **render_kwargs)
+            rgbs[i].copy_(rgb, non_blocking=True)
+            depth = (depth - near) / (far - near)
+            depths[i].copy_(depth, non_blocking=True)
+            if want_psnr:
+                gt = torch.as_tensor(gt_imgs[i]).to(dev, non_blocking=True).float()
+                ops.image_sqerr(rgb, gt[..., :3], out=sq[i])
+            if savedir is not None:
+                rgb8s.append((ops.to8b(rgb).cpu(), ops.to8b(depth).cpu()))
+    torch.cuda.synchronize(dev)
+    rgbs, depths = rgbs.numpy(), depths.numpy()
+    if savedir is not None and parallel.rank(group) == 0:
+        os.makedirs(savedir, exist_ok=True)
+        for i, (c8, d8) in enumerate(rgb8s):
+            _write_png(os.path.join(savedir, "{:03d}.png".format(i)), c8.numpy())
+            _write_png(os.path.join(savedir, "depth_{:03d}.png".format(i)), d8.numpy())
+    if want_psnr:
+        psnrs = (-10. * torch.log10(sq / float(H * W * 3))).cpu().tolist()
+        avg_psnr = sum(psnrs) / len(psnrs)
+        print("Avg PSNR over Test set: ", avg_psnr)
+        if savedir is not None and parallel.rank(group) == 0:
+            with open(os.path.join(savedir, "test_psnrs_avg{:0.2f}.pkl".format(avg_psnr)), "wb") as fp:
+                pickle.dump(psnrs, fp)
+        render_path.last_psnrs = psnrs
+    return rgbs, depths
+
+
 def patch(run_nerf_module):
     """Install the renderer into an imported reference driver (`import run_nerf; patch(run_nerf)`):
     the driver's train()/render_path() then run on the kernels.  See INTEGRATION.md."""
-    for name in ("batchify", "run_network", "batchify_rays", "render", "raw2outputs", "render_rays"):
+    for name in ("batchify", "run_network", "batchify_rays", "render", "raw2outputs", "render_rays", "render_path"):
         setattr(run_nerf_module, name, globals()[name])
     return run_nerf_module

@@ -9,6 +9,7 @@
 #include "../../indoor-nerf_b200/csrc/hash_core.cuh"
 #include "../../indoor-nerf_b200/csrc/ray_core.cuh"
 #include "../../indoor-nerf_b200/csrc/sample_core.cuh"
+#include "../../indoor-nerf_b200/csrc/io_core.cuh"
 
 using namespace pn;
 
@@ -108,6 +109,61 @@ void emu_ndc_rays(int H, int W, double focal, double near, const float *o, const
                   float *od) {
   const float cw = (float)(-1.0 / (W / (2.0 * focal))), ch = (float)(-1.0 / (H / (2.0 * focal)));
   for (int64_t p = 0; p < n; ++p) ndc_ray(cw, ch, (float)near, (float)(2.0 * near), o + 3 * p, d + 3 * p, oo + 3 * p, od + 3 * p);
+}
+
+// ---- data formats either side of the path (io_core.cuh) -------------------------------------------------------
+void emu_ray_bank(const int64_t *ids, int64_t B, int H, int W, const double *K, const float *poses, int64_t pose_stride,
+                  const int32_t *image_index, const float *images, int f64_dirs, float *rays, float *target) {
+  CamF64 cam;
+  cam.fx = K[0]; cam.cx = K[2]; cam.fy = K[4]; cam.cy = K[5];
+  const int64_t hw = (int64_t)H * W;
+  for (int64_t b = 0; b < B; ++b) {
+    const int64_t slot = ids[b] / hw, pix = ids[b] - slot * hw;
+    const int j = (int)(pix / W), i = (int)(pix - (int64_t)j * W);
+    const int64_t img = image_index ? image_index[slot] : slot;
+    const float *c2w = poses + img * pose_stride;
+    float d[3];
+    if (f64_dirs) ray_dir_f64(cam, c2w, 4, i, j, d);
+    else ray_dir_f32(cam, c2w, 4, i, j, d);
+    for (int c = 0; c < 3; ++c) {
+      rays[3 * b + c] = c2w[4 * c + 3];
+      rays[3 * (B + b) + c] = d[c];
+      if (target) target[3 * b + c] = images[(img * hw + pix) * 3 + c];
+    }
+  }
+}
+
+void emu_to8b(const float *x, int64_t n, uint8_t *out) {
+  for (int64_t k = 0; k < n; ++k) out[k] = to8b_one(x[k]);
+}
+
+void emu_quant_pack(const float *x, int64_t n, const float *qrow, int bits, uint32_t *words) {
+  for (int64_t g = 0; g < n / 32; ++g) {
+    uint32_t code[32];
+    for (int e = 0; e < 32; ++e) code[e] = quant_code(x[g * 32 + e], qrow[1], qrow[2], qrow[3], qrow[4]);
+    pack32(code, bits, words + g * bits);
+  }
+}
+
+void emu_quant_unpack(const uint32_t *words, int64_t n, const float *qrow, int bits, float *x) {
+  for (int64_t k = 0; k < n; ++k)
+    x[k] = quant_value(unpack_one(words + (k >> 5) * bits, (int)(k & 31), bits), qrow[0], qrow[2], qrow[3]);
+}
+
+double emu_ssim_sum(const float *a, const float *b, int H, int W, int C, double data_range) {
+  double tot = 0.0;
+  for (int c = 0; c < C; ++c)
+    for (int y = 0; y + 7 <= H; ++y)
+      for (int x = 0; x + 7 <= W; ++x) {
+        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        for (int dy = 0; dy < 7; ++dy)
+          for (int dx = 0; dx < 7; ++dx) {
+            const double u = a[((int64_t)(y + dy) * W + x + dx) * C + c], v = b[((int64_t)(y + dy) * W + x + dx) * C + c];
+            sx += u; sy += v; sxx += u * u; syy += v * v; sxy += u * v;
+          }
+        tot += ssim_from_sums(sx, sy, sxx, syy, sxy, 49, data_range);
+      }
+  return tot;
 }
 
 }  // extern "C"

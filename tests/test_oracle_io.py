@@ -1,0 +1,127 @@
+"""The oracle of the data formats either side of the path (oracle/dataio_oracle.py) against the golden vectors
+the live reference produced (oracle/make_golden_io.py), and the host build of the kernels' per-element
+arithmetic (csrc/io_core.cuh via tests/hostemu) against both.  No GPU needed."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import dataio_oracle as D
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "hostemu")
+QROW = 8
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(EMU_DIR, "libhostemu.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17",
+                           "-I/usr/local/cuda/include", "-Wno-unknown-pragmas", "-o", so,
+                           os.path.join(EMU_DIR, "hostemu.cpp")])
+    lib = ctypes.CDLL(so)
+    lib.emu_ssim_sum.restype = ctypes.c_double
+    return lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def qrow_of(scale, zp, qmin, qmax):
+    scale = np.float32(scale)
+    return np.array([scale, np.float32(scale + np.float32(1e-8)), zp, qmin, qmax, 1, 0, 0], np.float32)
+
+
+# ---- ray bank -------------------------------------------------------------------------------------------------------
+def test_oracle_ray_bank_matches_reference(golden):
+    g = golden("ray_bank")
+    H, W, K = int(g["H"]), int(g["W"]), g["K"]
+    bank = D.rays_rgb_bank(H, W, K, g["poses"], g["images"], list(g["i_train"]))
+    assert bank.dtype == np.float32 and (bank == g["unshuffled"]).all()
+    np.random.seed(0)
+    order = D.shuffle_order(bank.shape[0])
+    assert (order == g["order"]).all() and (bank[order] == g["shuffled"]).all()
+    rays, tgt = D.batch_from_bank(g["shuffled"], 32, 16)
+    assert rays.shape == (2, 16, 3) and (tgt == g["shuffled"][32:48, 2]).all()
+
+
+@pytest.mark.parametrize("f64", [1, 0])
+def test_hostemu_ray_bank(emu, golden, f64):
+    g = golden("ray_bank")
+    H, W, K = int(g["H"]), int(g["W"]), np.ascontiguousarray(g["K"], np.float64)
+    poses, images = np.ascontiguousarray(g["poses"]), np.ascontiguousarray(g["images"])
+    idx = np.ascontiguousarray(g["i_train"], np.int32)
+    ids = np.ascontiguousarray(g["order"], np.int64)
+    B = ids.size
+    rays, tgt = np.zeros((2, B, 3), np.float32), np.zeros((B, 3), np.float32)
+    emu.emu_ray_bank(ptr(ids), ctypes.c_int64(B), H, W, ptr(K), ptr(poses), ctypes.c_int64(16), ptr(idx), ptr(images),
+                     f64, ptr(rays), ptr(tgt))
+    assert (tgt == g["shuffled"][:, 2]).all() and (rays[0] == g["shuffled"][:, 0]).all()
+    if f64:
+        assert (rays[1] == g["shuffled"][:, 1]).all()                       # bit-exact get_rays_np + astype
+    else:
+        # the float32 arithmetic of get_rays: same rays to float32 rounding, and bit-equal to the oracle's get_rays
+        assert np.abs(rays[1] - g["shuffled"][:, 1]).max() < 1e-6
+        import torch
+        from oracle import hashnerf_oracle as O
+        for n, img in enumerate(idx):
+            ro, rd = O.get_rays(H, W, K, torch.from_numpy(poses[img, :3, :4]))
+            sel = np.nonzero(ids // (H * W) == n)[0]
+            pix = ids[sel] % (H * W)
+            assert (rays[1][sel] == rd.reshape(-1, 3).numpy()[pix]).all()
+
+
+# ---- evaluation -----------------------------------------------------------------------------------------------------
+def test_oracle_psnr_and_to8b(emu, golden):
+    g = golden("eval_psnr")
+    assert D.psnr_render_path(g["rgb"], g["gt"]) == pytest.approx(float(g["p_render_path"]), rel=1e-7)
+    assert float(g["p_eval"]) == pytest.approx(float(g["p_render_path"]), rel=1e-5)
+    assert (D.to8b(g["rgb"]) == g["rgb8"]).all()
+    x = np.ascontiguousarray(np.concatenate([g["rgb"].reshape(-1), np.float32([-0.5, 0, 1, 1.5, 0.999999, 1 / 255, 0.00392])]))
+    out = np.zeros(x.size, np.uint8)
+    emu.emu_to8b(ptr(x), ctypes.c_int64(x.size), ptr(out))
+    assert (out == D.to8b(x)).all()
+
+
+def test_oracle_ssim_known_answers(emu):
+    rs = np.random.RandomState(0)
+    a = rs.rand(12, 11, 3).astype(np.float32)
+    b = np.clip(a + rs.randn(12, 11, 3).astype(np.float32) * 0.1, 0, 1).astype(np.float32)
+    assert D.ssim(a, a) == pytest.approx(1.0, abs=1e-6)
+    brute = D.ssim_bruteforce(a, b)
+    assert D.ssim(a, b) == pytest.approx(brute, abs=2e-5)                  # float32 uniform_filter vs float64 windows
+    assert D.ssim(a.astype(np.float64), b.astype(np.float64)) == pytest.approx(brute, abs=1e-12)
+    s = emu.emu_ssim_sum(ptr(a), ptr(b), 12, 11, 3, ctypes.c_double(1.0))
+    assert s / (6 * 5 * 3) == pytest.approx(brute, abs=1e-12)
+    const = np.full((9, 9, 1), 0.25, np.float32)
+    assert D.ssim_bruteforce(const, const * 2) == pytest.approx((2 * .25 * .5 + 1e-4) / (.25 ** 2 + .5 ** 2 + 1e-4), rel=1e-9)
+
+
+# ---- A-CAQ export ----------------------------------------------------------------------------------------------------
+CASES = [("asym", k, False, "table") for k in range(6)] + [("sym", k, True, "w0") for k in range(3)]
+
+
+@pytest.mark.parametrize("tag,k,sym,src", CASES)
+def test_quant_codes_roundtrip(emu, golden, tag, k, sym, src):
+    g = golden("quant_export")
+    x = np.ascontiguousarray(g[src])
+    pre = "%s_%d_" % (tag, k)
+    bits, scale, zp, qmin, qmax = D.lbq_eval_params(g[pre + "bits"], g[pre + "range_scale"], g[pre + "v_max"], sym)
+    assert bits == int(round(float(g[pre + "bits"])))
+    codes = D.quant_codes(x, scale, zp, qmin, qmax)
+    assert codes.min() >= 0 and codes.max() < 2 ** bits
+    assert (D.dequant_codes(codes, scale, zp, qmin) == g[pre + "out"]).all()         # oracle == reference, bit for bit
+    words = D.pack_bits(codes, bits)
+    assert words.size == x.size * bits // 32
+    assert (D.unpack_bits(words, bits, x.size) == codes).all()
+    # the kernels' arithmetic (host build): same words, same values
+    row = qrow_of(scale, zp, qmin, qmax)
+    w2 = np.zeros_like(words)
+    emu.emu_quant_pack(ptr(x), ctypes.c_int64(x.size), ptr(row), bits, ptr(w2))
+    assert (w2 == words).all()
+    y = np.zeros_like(x)
+    emu.emu_quant_unpack(ptr(w2), ctypes.c_int64(x.size), ptr(row), bits, ptr(y))
+    assert (y == g[pre + "out"]).all()
