@@ -57,6 +57,8 @@ class ClockSampler:
         self.t1 = time.time()
 
     def __enter__(self):
+        if self.index is None:                  # ranks other than 0 do not sample
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -204,6 +206,90 @@ def fp32_mode_leg(pn, step_resident):
         pn.set_mlp_mode(MLP_MODE)
 
 
+def hash_t22_leg(pn, ops, pts, dev, peak):
+    """BASELINE configs[3] table size (log2_hashmap 22: 512 MiB of tables, 4x the L2): the hash-encode kernels where the
+    table set cannot be L2-resident, same ray-ordered points."""
+    try:
+        box = (pts.min(0)[0].cpu() - 0.1, pts.max(0)[0].cpu() + 0.1)
+        emb = pn.HashEmbedder(box, log2_hashmap_size=22, finest_resolution=512).to(dev)
+        tables = [t.detach() for t in emb.tables()]
+        P = pts.shape[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.no_grad():
+            for _ in range(2):
+                ops.hash_encode_fwd(emb.grid(), tables, pts)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                ops.hash_encode_fwd(emb.grid(), tables, pts)
+            e1.record()
+            torch.cuda.synchronize()
+            tf = e0.elapsed_time(e1) / 5
+            dfeat = torch.randn(P, 32, device=dev)
+            flat = torch.zeros(16, 1 << 22, 2, device=dev)
+            ops.hash_encode_bwd(emb.grid(), list(flat.unbind(0)), pts, dfeat)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                ops.hash_encode_bwd(emb.grid(), list(flat.unbind(0)), pts, dfeat)
+            e1.record()
+            torch.cuda.synchronize()
+            tb = e0.elapsed_time(e1) / 5
+        ach = HASH_BYTES_PER_POINT * P / (tf * 1e-3) / 1e9
+        return {"kernel": "hash_fwd_kernel", "log2_hashmap_size": 22, "table_bytes": 16 * (1 << 22) * 8,
+                "points_per_launch": P, "ms_per_launch": tf, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "bound": "hbm",
+                "backward": {"kernel": "hash_bwd_kernel", "ms_per_launch": tb,
+                             "achieved": HASH_BYTES_PER_POINT * P / (tb * 1e-3) / 1e9},
+                "note": "algorithmic bytes (8 B per gathered corner); the table set is 4x the L2, so the fine levels "
+                        "miss it and every 8-byte gather moves a 32-byte DRAM sector"}
+    except Exception as ex:
+        return {"error": repr(ex)}
+
+
+def io_legs(pn, scene, kw2, scene2, dev):
+    """on-GPU ray batching (rays/s of batch generation, bank bytes vs the reference's precomputed
+    tensor) and test-set evaluation through render_path (frames to pinned host memory + on-device PSNR)."""
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        n_img = 100
+        images = torch.rand(n_img, scene["H"], scene["W"], 3, device=dev)
+        bank = pn.RayBank(scene["H"], scene["W"], scene["K"], scene["poses"], images, list(range(n_img)), device=dev)
+        bank.shuffle()
+        for _ in range(3):
+            bank.next_batch(RAYS_PER_RANK)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            bank.next_batch(RAYS_PER_RANK)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 20
+        out["ray_bank"] = {"rays_per_s": RAYS_PER_RANK / (t * 1e-3), "ms_per_batch": t, "batch": RAYS_PER_RANK,
+                           "bytes": bank.bytes_resident(),
+                           "what": "use_batching batches generated from (image, pixel) ids, 100 views of 400x400"}
+        del bank, images
+    except Exception as ex:
+        out["ray_bank"] = {"error": repr(ex)}
+    try:
+        poses = torch.from_numpy(scene2["poses"][:3])
+        gts = torch.rand(3, 800, 800, 3)
+        kw = dict(kw2, near=2., far=6.)
+        hwf = [800, 800, scene2["focal"]]
+        pn.render_path(poses[:1], hwf, scene2["K"], 1 << 17, kw, gt_imgs=gts[:1])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pn.render_path(poses, hwf, scene2["K"], 1 << 17, kw, gt_imgs=gts)
+        dt = (time.perf_counter() - t0) / 3
+        out["render_path"] = {"mpix_per_s": 0.64 / dt, "ms_per_frame": dt * 1e3, "d2h_bytes_per_frame": 800 * 800 * 16,
+                              "what": "render_path over 3 test views of configs[1] incl. host copies of rgb/depth and "
+                                      "on-device PSNR against host ground truth (wall clock, synchronised)"}
+    except Exception as ex:
+        out["render_path"] = {"error": repr(ex)}
+    return out
+
+
 def run_ours(args):
     import indoor_nerf_b200 as pn
     from indoor_nerf_b200 import _lib, model as pmodel, ops, synthetic
@@ -236,7 +322,7 @@ def run_ours(args):
         loss, _ = tr.step(r.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
         losses.append(loss.item())
 
-    with ClockSampler(local) as clk:
+    with ClockSampler(local if rank == 0 else None) as clk:
         for i in range(args.warmup):
             step_e2e(i)
         torch.cuda.synchronize()
@@ -294,7 +380,7 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             t_bwd = e0.elapsed_time(e1) / reps
-            del dfeat, flat, pts, z
+            del dfeat, flat, z
         peak, how = peaks()
         ach = HASH_BYTES_PER_POINT * P / (t_fwd * 1e-3) / 1e9
         line["roofline"] = {"kernel": "hash_fwd_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -304,6 +390,9 @@ def run_ours(args):
                             "backward": {"kernel": "hash_bwd_kernel", "ms_per_launch": t_bwd,
                                          "achieved": HASH_BYTES_PER_POINT * P / (t_bwd * 1e-3) / 1e9}}
         line["roofline"]["traffic"] = 1.890e9 if P == 12582912 else None   # ncu dram bytes read+write per launch (profiles/r01_ncu_full_hash_fwd_mlp_fwd_fp32.csv)
+        line["roofline_t22"] = hash_t22_leg(pn, ops, pts, dev, peak)
+        del pts
+        torch.cuda.empty_cache()
         # ---- the fused field kernels of the bf16 mode (what the training step actually launches) ---------
         if MLP_MODE == "bf16":
             try:
@@ -368,6 +457,7 @@ def run_ours(args):
             t_frame = e0.elapsed_time(e1) / 3
             line["render"] = {"workload": "BASELINE configs[1]: 800x800 test view, finest_res 1024, 64+128 samples",
                               "mpix_per_s": 0.64 / (t_frame * 1e-3), "ms_per_frame": t_frame}
+            line.update(io_legs(pn, scene, kw2, scene2, dev))
             del kw2
         except Exception as ex:                                     # keep the headline even if this leg fails
             line["render"] = {"error": repr(ex)}
