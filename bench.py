@@ -290,6 +290,54 @@ def io_legs(pn, scene, kw2, scene2, dev):
     return out
 
 
+def render_t22_leg(pn, pmodel, synthetic, dev):
+    """Test-view rendering at the ScanNet-config table size (log2_hashmap 22, 512 MiB of fp32 tables = 4x the L2) with a
+    quantised (A-CAQ, 8-bit) model: gathering fp32 entries, fake-quantising them in the gather (the reference's eval
+    semantics), and gathering u8 codes (HashEmbedder.pack_for_inference: 128 MiB; same embeddings bit for bit in the fp32 mode,
+    within fp32 rounding before the bf16 cast in this mode)."""
+    try:
+        sc = synthetic.blender_scene(800, 800, n_views=2)
+        a = pmodel.default_args(bounding_box=sc["bounding_box"], finest_res=1024, log2_hashmap_size=22,
+                                use_quantization=True, quantization_bits=8)
+        _, kw, _, _, _ = pmodel.create_nerf(a, device=dev)
+        emb, nets = kw["embed_fn"], [kw["network_fn"], kw["network_fine"]]
+        for l, q in enumerate(emb.quantizers):
+            q.calibrate(emb.embeddings[l].weight.detach())
+        for n in nets:
+            n.sigma_weight_quantizer.calibrate(n.sigma_net[0].weight.detach())
+            n.sigma_act_quantizers[0].calibrate(torch.tensor([-0.5, 0.5], device=dev))   # non-degenerate zero point
+            n.eval()
+        emb.eval()
+        c2w = torch.from_numpy(sc["poses"][0][:3, :4])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def mpix():
+            def frame():
+                with torch.no_grad():
+                    return pn.render(800, 800, sc["K"], chunk=1 << 17, c2w=c2w, near=2., far=6., **kw)[0]
+            frame(); frame()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                img = frame()
+            e1.record()
+            torch.cuda.synchronize()
+            return 0.64 / (e0.elapsed_time(e1) / 3 * 1e-3), img
+
+        out = {"workload": "800x800 test view, log2_hashmap 22, finest_res 1024, 64+128 samples, 8-bit A-CAQ model"}
+        emb.use_quantization = False
+        out["fp32_tables_mpix_per_s"], _ = mpix()
+        emb.use_quantization = True
+        out["fake_quant_in_gather_mpix_per_s"], img_fq = mpix()
+        packed = emb.pack_for_inference()
+        out["u8_codes_mpix_per_s"], img_pk = mpix()
+        out["max_abs_frame_diff_codes_vs_fake_quant"] = float((img_fq - img_pk).abs().max())
+        out["table_bytes"] = {"fp32": 16 * (1 << 22) * 8, "codes": packed.nbytes()}
+        return out
+    except Exception as ex:
+        return {"error": repr(ex)}
+
+
 def run_ours(args):
     import indoor_nerf_b200 as pn
     from indoor_nerf_b200 import _lib, model as pmodel, ops, synthetic
@@ -459,6 +507,8 @@ def run_ours(args):
                               "mpix_per_s": 0.64 / (t_frame * 1e-3), "ms_per_frame": t_frame}
             line.update(io_legs(pn, scene, kw2, scene2, dev))
             del kw2
+            torch.cuda.empty_cache()
+            line["render_t22_quantised"] = render_t22_leg(pn, pmodel, synthetic, dev)
         except Exception as ex:                                     # keep the headline even if this leg fails
             line["render"] = {"error": repr(ex)}
         torch.cuda.empty_cache()

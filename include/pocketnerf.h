@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 7
+#define PN_ABI_VERSION 8
 #define PN_MAX_LEVELS 16
 
 #define PN_EINVAL (-1)   /* bad argument */
@@ -298,6 +298,34 @@ int pn_to8b(const float *x, int64_t n, uint8_t *out, pn_stream_t stream);
  * pn_quant_unpack writes (code + qmin - zp) * scale, bit-identical to the quantiser's eval output on x. */
 int pn_quant_pack(const float *x, int64_t n, const float *qrow, int bits, uint32_t *words, pn_stream_t stream);
 int pn_quant_unpack(const uint32_t *words, int64_t n, const float *qrow, int bits, float *x, pn_stream_t stream);
+
+/* Hash tables resident as integer codes (inference with a trained A-CAQ model).  Level l holds 2^log2_hashmap_size
+ * entries; an entry is the pair of feature codes as two u8 (entry_bytes 2: learned width <= 8 bits), two u16
+ * (entry_bytes 4: <= 16 bits), little endian, feature 0 first — or two fp32 values already dequantised (entry_bytes 8).
+ * A code c stands for (c + qmin - zero_point) * scale, the value LearnedBitwidthQuantizer's eval forward gives the
+ * fp32 entry (quantization.py:183-186), so gathering codes reproduces hash_encoding.py:97-101 in eval mode bit for
+ * bit while moving 2-4 bytes per corner instead of 8. */
+typedef struct {
+  const void *codes[PN_MAX_LEVELS];     /* device */
+  int32_t entry_bytes[PN_MAX_LEVELS];   /* 2, 4 or 8 */
+  float scale[PN_MAX_LEVELS];
+  float zero_point[PN_MAX_LEVELS];
+  float qmin[PN_MAX_LEVELS];
+} pn_packed_tables;
+
+/* pn_hash_encode_fwd on code tables (no gradient: inference). */
+int pn_hash_encode_fwd_packed(const pn_hash_grid *grid, const pn_packed_tables *packed, const float *x,
+                              int64_t n_points, float *feat, uint8_t *keep, pn_stream_t stream);
+/* pn_field_fwd_bf16 on code tables (no feature tiles are saved: inference). */
+int pn_field_fwd_bf16_packed(const pn_hash_grid *grid, const pn_packed_tables *packed, const pn_mlp_weights *w,
+                             const float *pts, const float *dirs, int samples_per_ray, const float *act_q,
+                             int64_t n_points, float *out, uint8_t *keep, pn_stream_t stream);
+
+/* Container codes for pn_packed_tables: out[k] = code of x[k] as u8 (code_bytes 1) or u16 (code_bytes 2), from the
+ * fp32 values (pn_quant_codes, qrow = the quantiser's eval-form row) or from a pn_quant_pack bit stream
+ * (pn_quant_unpack_codes; bits <= 8*code_bytes, n % 32 == 0). */
+int pn_quant_codes(const float *x, int64_t n, const float *qrow, int code_bytes, void *out, pn_stream_t stream);
+int pn_quant_unpack_codes(const uint32_t *words, int64_t n, int bits, int code_bytes, void *out, pn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpocketnerf.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_LEVELS = 16
 QROW = 8
 
@@ -34,6 +34,12 @@ class MlpInput(ctypes.Structure):
     _fields_ = [("feat", ctypes.c_void_p), ("feat_stride", ctypes.c_int64), ("sh", ctypes.c_void_p),
                 ("sh_stride", ctypes.c_int64), ("dirs", ctypes.c_void_p), ("samples_per_ray", ctypes.c_int32),
                 ("act_q", ctypes.c_void_p), ("keep", ctypes.c_void_p), ("n_points", ctypes.c_int64)]
+
+
+class PackedTables(ctypes.Structure):
+    _fields_ = [("codes", ctypes.c_void_p * MAX_LEVELS), ("entry_bytes", ctypes.c_int32 * MAX_LEVELS),
+                ("scale", ctypes.c_float * MAX_LEVELS), ("zero_point", ctypes.c_float * MAX_LEVELS),
+                ("qmin", ctypes.c_float * MAX_LEVELS)]
 
 
 _P, _I, _L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
@@ -72,6 +78,11 @@ _SIGNATURES = {
     "pn_to8b": [_P, _L, _P, _P],
     "pn_quant_pack": [_P, _L, _P, _I, _P, _P],
     "pn_quant_unpack": [_P, _L, _P, _I, _P, _P],
+    "pn_quant_codes": [_P, _L, _P, _I, _P, _P],
+    "pn_quant_unpack_codes": [_P, _L, _I, _I, _P, _P],
+    "pn_hash_encode_fwd_packed": [ctypes.POINTER(HashGrid), ctypes.POINTER(PackedTables), _P, _L, _P, _P, _P],
+    "pn_field_fwd_bf16_packed": [ctypes.POINTER(HashGrid), ctypes.POINTER(PackedTables), ctypes.POINTER(MlpWeights), _P, _P,
+                                 _I, _P, _L, _P, _P, _P],
 }
 # entry points added by later kernels (fused field, tensor-core MLP, optimizer); bound when exported
 _OPTIONAL = {}

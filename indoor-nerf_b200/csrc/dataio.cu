@@ -161,6 +161,22 @@ __global__ void quant_unpack_kernel(const uint32_t *__restrict__ words, int64_t 
   x[k] = quant_value(code, scale, zp, qmin);
 }
 
+// thread = one value -> one u8 / u16 container code (tables resident as codes for inference)
+template <typename CODE>
+__global__ void quant_codes_kernel(const float *__restrict__ x, int64_t n, const float *__restrict__ qrow,
+                                   CODE *__restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  out[k] = (CODE)quant_code(x[k], qrow[1], qrow[2], qrow[3], qrow[4]);
+}
+
+template <typename CODE>
+__global__ void quant_unpack_codes_kernel(const uint32_t *__restrict__ words, int64_t n, int bits, CODE *__restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  out[k] = (CODE)unpack_one(words + (k >> 5) * bits, (int)(k & 31), bits);
+}
+
 }  // namespace pn
 
 using namespace pn;
@@ -246,4 +262,30 @@ extern "C" int pn_quant_unpack(const uint32_t *words, int64_t n, const float *qr
   quant_unpack_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(words, n, qrow, bits, x);
   count_launch();
   return check_launch("quant_unpack_kernel");
+}
+
+extern "C" int pn_quant_codes(const float *x, int64_t n, const float *qrow, int code_bytes, void *out,
+                              pn_stream_t stream) {
+  PN_REQUIRE(x && qrow && out, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(code_bytes == 1 || code_bytes == 2, PN_ESHAPE, "code_bytes %d (1 or 2)", code_bytes);
+  if (n <= 0) return 0;
+  const unsigned grid = (unsigned)ceil_div(n, 256);
+  if (code_bytes == 1) quant_codes_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>(x, n, qrow, (uint8_t *)out);
+  else quant_codes_kernel<uint16_t><<<grid, 256, 0, as_stream(stream)>>>(x, n, qrow, (uint16_t *)out);
+  count_launch();
+  return check_launch("quant_codes_kernel");
+}
+
+extern "C" int pn_quant_unpack_codes(const uint32_t *words, int64_t n, int bits, int code_bytes, void *out,
+                                     pn_stream_t stream) {
+  PN_REQUIRE(words && out, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(code_bytes == 1 || code_bytes == 2, PN_ESHAPE, "code_bytes %d (1 or 2)", code_bytes);
+  PN_REQUIRE(bits >= 1 && bits <= 8 * code_bytes, PN_ESHAPE, "bits %d do not fit %d-byte codes", bits, code_bytes);
+  PN_REQUIRE(n >= 0 && n % 32 == 0, PN_ESHAPE, "n %lld is not a multiple of 32", (long long)n);
+  if (n == 0) return 0;
+  const unsigned grid = (unsigned)ceil_div(n, 256);
+  if (code_bytes == 1) quant_unpack_codes_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>(words, n, bits, (uint8_t *)out);
+  else quant_unpack_codes_kernel<uint16_t><<<grid, 256, 0, as_stream(stream)>>>(words, n, bits, (uint16_t *)out);
+  count_launch();
+  return check_launch("quant_unpack_codes_kernel");
 }

@@ -110,6 +110,15 @@ PN_HD float fake_quant(float x, float scale, float denom, float zp, float qmin, 
   return train_form ? pn_add(x, pn_sub(dq, x)) : dq;
 }
 
+// The same fake-quant for the bf16 paths: multiply by the reciprocal of the divisor instead of an IEEE division (the
+// rounded integer can differ from the exact form only when x/denom + zp sits within an ulp of a tie).
+PN_HD float fake_quant_fast(float x, float scale, float rdenom, float zp, float qmin, float qmax, bool train_form) {
+  float q = rintf(x * rdenom + zp);
+  q = fminf(fmaxf(q, qmin), qmax);
+  const float dq = (q - zp) * scale;
+  return train_form ? x + (dq - x) : dq;
+}
+
 // contraction-friendly trilinear interpolation for the bf16 paths
 PN_HD float trilerp_fast(const float e[8], const float w[3]) {
   const float c00 = e[0] + w[0] * (e[4] - e[0]), c01 = e[1] + w[0] * (e[5] - e[1]);

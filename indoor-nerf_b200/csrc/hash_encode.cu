@@ -10,6 +10,7 @@
 // 128-byte lines.  HBM traffic per point is then the algorithmic minimum 12 B in + 128 B out.
 #include "hash_core.cuh"
 #include "hash_scatter.cuh"
+#include "io_core.cuh"
 
 namespace pn {
 
@@ -204,6 +205,65 @@ int check_grid_args(const pn_hash_grid *g) {
   return 0;
 }
 
+// The same forward with the tables held as integer codes of the A-CAQ quantisers (eval form): each gathered
+// entry is 2 or 4 bytes instead of 8, decoded as (code + qmin - zp) * scale — bit-identical to fake-quantising the
+// fp32 entry (quantization.py:183-186), so feat equals the quantised reference's eval-mode output.  At T = 2^22
+// the 512 MiB fp32 table set shrinks to 128 MiB (8-bit levels), which the 126 MB L2 nearly holds.
+__global__ void __launch_bounds__(kHashThreads)
+hash_fwd_packed_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ PackedDev T,
+                       const float *__restrict__ x, int64_t P, float *__restrict__ feat, uint8_t *__restrict__ keep) {
+  __shared__ float stage[kHashWarps][32 * kStagePitch];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int F = 2 * G.n_levels;
+  float *st = stage[warp];
+  for (int64_t base = ((int64_t)blockIdx.x * kHashWarps + warp) * 32; base < P;
+       base += (int64_t)gridDim.x * kHashThreads) {
+    const int64_t p = base + lane;
+    const bool valid = p < P;
+    float xv[3] = {0.f, 0.f, 0.f};
+    if (valid) load_point(x, p, xv);
+#pragma unroll 2
+    for (int l = 0; l < G.n_levels; ++l) {
+      Cell c;
+      point_cell(G, l, xv, c);
+      float e0[8], e1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) packed_entry<true>(T, l, corner_index(G, c, k), e0[k], e1[k]);
+      st[lane * kStagePitch + 2 * l + 0] = trilerp(e0, c.w);
+      st[lane * kStagePitch + 2 * l + 1] = trilerp(e1, c.w);
+    }
+    if (valid && keep) keep[p] = point_keep(G, xv) ? 1 : 0;
+    __syncwarp();
+    const int64_t rows = (P - base) < 32 ? (P - base) : 32;
+    for (int i = lane; i < 32 * F; i += 32) {
+      const int row = i / F, col = i - row * F;
+      if (row < rows) feat[(base + row) * F + col] = st[row * kStagePitch + col];
+    }
+    __syncwarp();
+  }
+}
+
+int fill_packed(PackedDev &T, const pn_hash_grid *grid, const pn_packed_tables *packed) {
+  PN_REQUIRE(packed != nullptr, PN_EINVAL, "packed is NULL");
+  for (int l = 0; l < PN_MAX_LEVELS; ++l) {
+    const int s = l < grid->n_levels ? l : 0;
+    PN_REQUIRE(packed->codes[s] != nullptr, PN_EINVAL, "packed->codes[%d] is NULL", s);
+    const int eb = packed->entry_bytes[s];
+    PN_REQUIRE(eb == 2 || eb == 4 || eb == 8, PN_ESHAPE, "entry_bytes[%d] = %d (2, 4 or 8)", s, eb);
+    PN_REQUIRE(((uintptr_t)packed->codes[s] & (uintptr_t)(eb - 1)) == 0, PN_EINVAL, "packed->codes[%d] misaligned", s);
+    T.t[l] = packed->codes[s];
+    T.eb[l] = (uint8_t)eb;
+    T.scale[l] = packed->scale[s];
+    T.sub[l] = packed_sub_const(packed->zero_point[s], packed->qmin[s]);
+    if (eb != 8) {
+      const float off = packed->qmin[s] - packed->zero_point[s];
+      PN_REQUIRE(off == rintf(off) && fabsf(off) < 4194304.f, PN_EINVAL, "level %d: qmin - zero_point = %g is not a small integer",
+                 s, (double)off);
+    }
+  }
+  return 0;
+}
+
 static int hash_blocks(int64_t P, int threads, int per_sm) {
   const int64_t need = ceil_div(P, threads);
   const int64_t cap = (int64_t)sm_count() * per_sm;
@@ -233,6 +293,21 @@ extern "C" int pn_hash_encode_fwd(const pn_hash_grid *grid, const float *const *
     hash_fwd_kernel<false><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, nullptr, x, n_points, feat, keep);
   count_launch();
   return check_launch("hash_fwd_kernel");
+}
+
+extern "C" int pn_hash_encode_fwd_packed(const pn_hash_grid *grid, const pn_packed_tables *packed, const float *x,
+                                         int64_t n_points, float *feat, uint8_t *keep, pn_stream_t stream) {
+  if (int e = check_grid_args(grid)) return e;
+  PN_REQUIRE(x && feat, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(n_points >= 0, PN_EINVAL, "n_points < 0");
+  PackedDev T;
+  if (int e = fill_packed(T, grid, packed)) return e;
+  if (n_points == 0) return 0;
+  const HashGridDev G = make_grid_dev(*grid);
+  const int blocks = hash_blocks(n_points, kHashThreads, 16);
+  hash_fwd_packed_kernel<<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, x, n_points, feat, keep);
+  count_launch();
+  return check_launch("hash_fwd_packed_kernel");
 }
 
 extern "C" int pn_hash_encode_bwd(const pn_hash_grid *grid, float *const *dtables, const float *x,

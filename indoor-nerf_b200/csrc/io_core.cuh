@@ -5,6 +5,8 @@
 //   * to8b, squared error and SSIM window statistics for test-set evaluation,
 //   * integer codes of the A-CAQ fake-quantiser and their bit-packing at the learned width.
 #pragma once
+#include <string.h>
+
 #include "hash_core.cuh"
 #include "ray_core.cuh"
 
@@ -69,6 +71,88 @@ PN_HD float quant_value(uint32_t code, float scale, float zp, float qmin) {
   const float q = pn_add((float)code, qmin);          // exact: |q| < 2^24
   return pn_mul(pn_sub(q, zp), scale);
 }
+
+// ---- hash tables held as integer codes (inference) -----------------------------------------------------------
+// Level l is an array of 2^T entries; an entry is the pair (feature 0, feature 1) as two u8 codes (2 bytes), two u16
+// codes (4 bytes) or two fp32 values (8 bytes, already dequantised: levels whose learned width exceeds 16 bits).
+//
+// Decode without an int->float conversion: with M = 1.5 * 2^23 = 0x4B400000, the bit pattern M | c IS the float
+// M + c for c < 2^22, so one byte permute builds it from the loaded word and one exact subtraction of the per-level
+// constant (M - (qmin - zp)) yields q - zp = c + qmin - zp — the same integer-valued float that
+// pn_sub(pn_add(float(c), qmin), zp) produces (all three are integers below 2^24, hence exact).  The value is then
+// (q - zp) * scale, rounded once: bit-identical to quant_value / to the quantiser's eval forward.
+struct PackedDev {
+  const void *t[PN_MAX_LEVELS];
+  float scale[PN_MAX_LEVELS];
+  float sub[PN_MAX_LEVELS];      // M - (qmin - zp), exact
+  uint8_t eb[PN_MAX_LEVELS];
+};
+
+#define PN_CODE_MAGIC 0x4B400000u   // 12582912.0f
+
+PN_HD float packed_sub_const(float zp, float qmin) { return pn_sub(12582912.0f, pn_sub(qmin, zp)); }
+
+PN_HD uint32_t pn_byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(x, y, s);
+#else
+  const uint64_t v = ((uint64_t)y << 32) | x;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+#endif
+}
+
+PN_HD float pn_bits_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+// q - zp of the two codes of one entry word (u8 pair in the low 16 bits, or u16 pair), as exact integer-valued floats
+PN_HD void packed_levels_q(uint32_t word, bool u16, float sub, float &d0, float &d1) {
+  const uint32_t p0 = pn_byte_perm(word, PN_CODE_MAGIC, u16 ? 0x7610u : 0x7650u);
+  const uint32_t p1 = pn_byte_perm(word, PN_CODE_MAGIC, u16 ? 0x7632u : 0x7651u);
+  d0 = pn_sub(pn_bits_float(p0), sub);
+  d1 = pn_sub(pn_bits_float(p1), sub);
+}
+
+// the dequantised pair of one entry word
+PN_HD void packed_decode(const PackedDev &T, int l, uint32_t word, bool u16, float &e0, float &e1) {
+  float d0, d1;
+  packed_levels_q(word, u16, T.sub[l], d0, d1);
+  const float scale = T.scale[l];
+  e0 = pn_mul(d0, scale);
+  e1 = pn_mul(d1, scale);
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t packed_word(const PackedDev &T, int l, uint32_t h, bool u16) {
+  return u16 ? __ldg(reinterpret_cast<const uint32_t *>(T.t[l]) + h)
+             : (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(T.t[l]) + h);
+}
+
+// EXACT = true : e = (q - zp) * scale per gathered value (fp32 path, bit-exact with the fake-quantised fp32 entry).
+// EXACT = false: e = q - zp; the caller interpolates in the code domain and multiplies the result by scale once
+//                (bf16 path: 16 multiplies per level become 2; differs from EXACT by fp32 rounding only).
+template <bool EXACT>
+__device__ __forceinline__ void packed_entry(const PackedDev &T, int l, uint32_t h, float &e0, float &e1) {
+  const int eb = T.eb[l];
+  if (eb == 8) {
+    const float2 e = __ldg(reinterpret_cast<const float2 *>(T.t[l]) + h);
+    e0 = e.x;
+    e1 = e.y;
+    return;
+  }
+  const uint32_t w = packed_word(T, l, h, eb == 4);
+  if (EXACT) packed_decode(T, l, w, eb == 4, e0, e1);
+  else packed_levels_q(w, eb == 4, T.sub[l], e0, e1);
+}
+#endif
 
 // 32 codes of `bits` bits each <-> `bits` little-endian 32-bit words (element e occupies stream bits [e*bits, (e+1)*bits)).
 PN_HD void pack32(const uint32_t code[32], int bits, uint32_t *words) {

@@ -7,6 +7,7 @@
 
 #include "hash_core.cuh"
 #include "hash_scatter.cuh"
+#include "io_core.cuh"
 #include "tc_common.cuh"
 
 namespace pn {
@@ -133,10 +134,11 @@ struct FieldArgs {
   uint8_t *keep_out;    // forward: [P]
   uint4 *featb;         // bf16 feature tiles, 8 KB per 128-point tile, tile layout (forward writes, backward reads)
   int scatter_split;    // backward: half 0 scatters levels [0, split), half 1 the rest
+  PackedDev PK;         // SRC_PACKED: tables as integer codes (inference)
 };
 
 // input source of a tile's hash features
-enum { SRC_F32 = 0, SRC_HASH = 1, SRC_TILE = 2 };
+enum { SRC_F32 = 0, SRC_HASH = 1, SRC_TILE = 2, SRC_PACKED = 3 };
 
 // fp32 [N x K] row-major global weight (ld = Kvalid) -> bf16 tile [NT x KT], zero padded
 __device__ void load_w_tile(uint8_t *tile, const float *__restrict__ W, int NT, int KT, int Nvalid, int Kvalid) {
@@ -195,6 +197,7 @@ constexpr int kTcThreads = 256;
 //   SRC_HASH: evaluated here from the point coordinates — 8 levels x 8 gathers per thread — and, when
 //             F.featb is set, also saved as bf16 tiles for the backward (pn_field_fwd_bf16)
 //   SRC_TILE: bf16 tile saved by the forward, copied as is (pn_field_bwd_bf16)
+//   SRC_PACKED: as SRC_HASH with the tables held as u8/u16 codes, decoded in the gather (pn_field_fwd_bf16_packed)
 template <int SRC>
 __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, const FieldArgs *F, int64_t tile,
                                                int64_t base, int p, int half, bool valid) {
@@ -231,28 +234,37 @@ __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, con
       if (l < F->G.n_levels && valid) {
         Cell c;
         point_cell<false>(F->G, l, xv, c);
-        const float2 *__restrict__ tab = F->T.t[l];
         float e0[8], e1[8];
+        if (SRC == SRC_PACKED) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const float2 e = __ldg(tab + corner_index(F->G, c, k)); e0[k] = e.x; e1[k] = e.y; }
-        if (F->qparams) {
+          for (int k = 0; k < 8; ++k) packed_entry<false>(F->PK, l, corner_index(F->G, c, k), e0[k], e1[k]);
+        } else {
+          const float2 *__restrict__ tab = F->T.t[l];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const float2 e = __ldg(tab + corner_index(F->G, c, k)); e0[k] = e.x; e1[k] = e.y; }
+        }
+        if (SRC == SRC_HASH && F->qparams) {
           const float *q = F->qparams + l * PN_QROW;
           if (q[5] != 0.f) {
-            const float scale = q[0], denom = q[1], zp = q[2], qmin = q[3], qmax = q[4];
+            const float scale = q[0], rdenom = 1.0f / q[1], zp = q[2], qmin = q[3], qmax = q[4];
             const bool train_form = q[6] != 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              e0[k] = fake_quant(e0[k], scale, denom, zp, qmin, qmax, train_form);
-              e1[k] = fake_quant(e1[k], scale, denom, zp, qmin, qmax, train_form);
+              e0[k] = fake_quant_fast(e0[k], scale, rdenom, zp, qmin, qmax, train_form);
+              e1[k] = fake_quant_fast(e1[k], scale, rdenom, zp, qmin, qmax, train_form);
             }
           }
         }
         f0 = trilerp_fast(e0, c.w);
         f1 = trilerp_fast(e1, c.w);
+        if (SRC == SRC_PACKED && F->PK.eb[l] != 8) {        // interpolated in the code domain: one scale per feature
+          f0 *= F->PK.scale[l];
+          f1 *= F->PK.scale[l];
+        }
       }
       *reinterpret_cast<uint32_t *>(sm + TS::A0 + chunk_off(p, l >> 2, 4) + (l & 3) * 4) = pack_bf16(f0, f1);
     }
-    if (F->featb) {
+    if (SRC == SRC_HASH && F->featb) {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const uint32_t off = chunk_off(p, half * 2 + c, 4);
@@ -424,7 +436,7 @@ mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__
       tmem_ld_wait();
       if (valid) {
         bool kept = A.in.keep ? (A.in.keep[base + p] != 0) : true;
-        if (SRC == SRC_HASH) {
+        if (SRC == SRC_HASH || SRC == SRC_PACKED) {
           const float xv[3] = {__ldg(F.pts + 3 * (base + p)), __ldg(F.pts + 3 * (base + p) + 1), __ldg(F.pts + 3 * (base + p) + 2)};
           kept = point_keep(F.G, xv);
         }
@@ -743,7 +755,7 @@ int check_mlp_args(const pn_mlp_weights *w, const pn_mlp_input *in, bool *normal
 namespace pn {
 int check_grid_args(const pn_hash_grid *g);                                            // hash_encode.cu
 
-static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float *out, cudaStream_t st) {
+static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float *out, cudaStream_t st, bool packed = false) {
   // without the normal head the NH tile (last block of the forward map) is not allocated: 55.5 KB -> 4 CTAs/SM
   const int smem = A.normals ? TS::FWD_END : TS::NH;
   // the fused variant carries the hash-gather state: at 4 CTAs/SM (64 registers) it spills and measured 25 %
@@ -753,7 +765,7 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
     const char *e = getenv("PN_FWD_CTAS");
     fused_ctas = (e && atoi(e) == 4) ? 4 : 3;
   }
-  const int per_sm = A.normals ? 3 : (fused ? fused_ctas : 4);   // x 128 TMEM columns each
+  const int per_sm = (A.normals || packed) ? 3 : (fused ? fused_ctas : 4);   // x 128 TMEM columns each
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -762,13 +774,15 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<4, SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<4, SRC_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_fwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int blocks = (int)(tiles < cap ? tiles : cap);
-  if (fused && per_sm == 4) mlp_tc_fwd_kernel<4, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  if (packed) mlp_tc_fwd_kernel<3, SRC_PACKED><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  else if (fused && per_sm == 4) mlp_tc_fwd_kernel<4, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   else if (fused) mlp_tc_fwd_kernel<3, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   else if (A.normals) mlp_tc_fwd_kernel<3, SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   else mlp_tc_fwd_kernel<4, SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, out);
@@ -896,4 +910,30 @@ extern "C" int pn_field_bwd_bf16(const pn_hash_grid *grid, float *const *dtables
   }
   F.scatter_split = split;
   return launch_tc_bwd(A, F, true, dout, nullptr, 32, nullptr, 16, *dw, as_stream(stream));
+}
+
+namespace pn {
+int fill_packed(PackedDev &T, const pn_hash_grid *grid, const pn_packed_tables *packed);   // hash_encode.cu
+}
+
+extern "C" int pn_field_fwd_bf16_packed(const pn_hash_grid *grid, const pn_packed_tables *packed, const pn_mlp_weights *w,
+                                        const float *pts, const float *dirs, int samples_per_ray, const float *act_q,
+                                        int64_t n_points, float *out, uint8_t *keep, pn_stream_t stream) {
+  PN_REQUIRE(w && packed && dirs && out, PN_EINVAL, "NULL pointer argument");
+  pn_mlp_input in = {};
+  in.feat = pts;            // placeholder for the shared argument check; never read
+  in.feat_stride = 32;
+  in.dirs = dirs; in.samples_per_ray = samples_per_ray; in.act_q = act_q; in.n_points = n_points;
+  bool normals = false;
+  PN_REQUIRE(((uintptr_t)pts & 15) == 0, PN_EINVAL, "pts must be 16-byte aligned");
+  if (int e = check_mlp_args(w, &in, &normals)) return e;
+  TcArgs A;
+  A.w = *w; A.in = in; A.normals = normals; A.C = normals ? 7 : 4;
+  PN_REQUIRE(A.C == 7 || ((uintptr_t)out & 15) == 0, PN_EINVAL, "out must be 16-byte aligned");
+  FieldArgs F = {};
+  if (int e = fill_field(F, grid, nullptr, nullptr, pts, nullptr)) return e;
+  if (int e = fill_packed(F.PK, grid, packed)) return e;
+  if (n_points == 0) return 0;
+  F.keep_out = keep;
+  return launch_tc_fwd(A, F, true, out, as_stream(stream), true);
 }

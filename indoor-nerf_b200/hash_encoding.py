@@ -62,6 +62,7 @@ class HashEmbedder(nn.Module):
             self.quantizers = None
         self._grid = None
         self._grid_key = None
+        self._packed = None                                       # ops.PackedLevels: tables as integer codes (inference)
 
     # -- storage management ---------------------------------------------------------------------------
     def _apply(self, fn, *args, **kwargs):
@@ -123,12 +124,50 @@ class HashEmbedder(nn.Module):
                     q.calibrate_minmax(mm[l, 0], mm[l, 1])
         return torch.stack([q.qrow(self.training) for q in self.quantizers]).contiguous()
 
+    # -- tables as integer codes (inference) ----------------------------------------------------------------------
+    def pack_for_inference(self):
+        """Hold every level as the integer codes of its quantiser's eval form (u8 pairs up to 8 learned bits, u16
+        pairs up to 16, dequantised fp32 above) and gather from those in eval mode: 2-4 bytes per corner instead of
+        8, same output bit for bit as the fake-quantised fp32 tables (hash_encoding.py:97-101 in eval mode).  The
+        copy is a snapshot: it is dropped when the module goes back to training."""
+        if not (self.use_quantization and self.quantizers is not None and all(q.calibrated for q in self.quantizers)):
+            raise RuntimeError("pack_for_inference needs calibrated table quantisers (use_quantization=True, trained)")
+        if not self._is_flat():
+            self._reflatten()
+        levels = []
+        with torch.no_grad():
+            for l, q in enumerate(self.quantizers):
+                row = q.qrow(training=False).contiguous()
+                bits = q.integer_bit_width
+                w = self.embeddings[l].weight.detach()
+                r = row.cpu().tolist()
+                if bits <= 16:
+                    t = ops.quant_codes(w, row, 1 if bits <= 8 else 2)
+                else:
+                    was = q.training
+                    q.eval()
+                    t = q(w).float().contiguous()
+                    q.train(was)
+                levels.append((t, r[0], r[2], r[3]))
+        self._packed = ops.PackedLevels(levels)
+        return self._packed
+
+    def set_packed(self, packed):
+        self._packed = packed
+
+    def train(self, mode=True):
+        if mode:
+            self._packed = None
+        return super().train(mode)
+
     def forward(self, x):
         if self.training:
             self.current_step += 1
         if not self._is_flat():
             self._reflatten()
         x = x.reshape(-1, 3)
+        if self._packed is not None and not self.training:
+            return ops.hash_encode_fwd_packed(self.grid(), self._packed, x.detach())
         qrows = self._quant_rows(x.detach())
         feat, keep = ops.HashEncodeFn.apply(x, self.grid(), qrows, *self.tables())
         return feat, keep

@@ -7,7 +7,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import HashGrid, MlpInput, MlpWeights, call, dptr, fcontig, stream
+from ._lib import HashGrid, MlpInput, MlpWeights, PackedTables, call, dptr, fcontig, stream
 
 _MLP_KEYS = ("s0", "s1", "c0", "c1", "c2", "n0w", "n0b", "n2w", "n2b")
 
@@ -652,3 +652,81 @@ def quant_unpack(words, n, qrow, bits):
     with _guard(words):
         call("pn_quant_unpack", dptr(words.contiguous(), torch.int32), n, dptr(fcontig(qrow)), int(bits), dptr(x), stream())
     return x
+
+
+# ---------------------------------------------------------------------------------------------------
+# hash tables resident as integer codes (inference with a trained A-CAQ model)
+# ---------------------------------------------------------------------------------------------------
+def quant_codes(x, qrow, code_bytes):
+    """u8 / u16 container codes of fp32 values under a quantiser's eval-form row."""
+    x = fcontig(x)
+    out = torch.empty(x.shape, dtype=torch.uint8 if code_bytes == 1 else torch.int16, device=x.device)
+    with _guard(x):
+        call("pn_quant_codes", dptr(x), x.numel(), dptr(fcontig(qrow)), int(code_bytes), dptr(out, out.dtype), stream())
+    return out
+
+
+def quant_unpack_codes(words, n, bits, code_bytes):
+    """u8 / u16 container codes from a pn_quant_pack bit stream."""
+    out = torch.empty((n,), dtype=torch.uint8 if code_bytes == 1 else torch.int16, device=words.device)
+    with _guard(words):
+        call("pn_quant_unpack_codes", dptr(words.contiguous(), torch.int32), n, int(bits), int(code_bytes),
+             dptr(out, out.dtype), stream())
+    return out
+
+
+class PackedLevels:
+    """Per-level code tensors + decode scalars in the form the kernels take (struct pn_packed_tables).
+    levels: list of (tensor, scale, zp, qmin); tensor is uint8 [T,2], int16 [T,2] (u16 codes) or float32 [T,2]."""
+
+    def __init__(self, levels):
+        if not 1 <= len(levels) <= _lib.MAX_LEVELS:
+            raise _lib.PocketNerfError("1..16 levels expected")
+        self.tensors = []
+        self.struct = PackedTables()
+        rows = levels[0][0].shape[0]
+        for l, (t, scale, zp, qmin) in enumerate(levels):
+            if not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != (rows, 2):
+                raise _lib.PocketNerfError("level %d: expected a contiguous CUDA [%d,2] tensor" % (l, rows))
+            eb = {torch.uint8: 2, torch.int16: 4, torch.float32: 8}.get(t.dtype)
+            if eb is None:
+                raise _lib.PocketNerfError("level %d: dtype %s (uint8, int16 or float32)" % (l, t.dtype))
+            self.tensors.append(t)
+            self.struct.codes[l] = t.data_ptr()
+            self.struct.entry_bytes[l] = eb
+            self.struct.scale[l], self.struct.zero_point[l], self.struct.qmin[l] = float(scale), float(zp), float(qmin)
+        self.rows = rows
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.tensors)
+
+
+def hash_encode_fwd_packed(grid, packed, x):
+    """hash_encode_fwd on code tables -> feat[P,2L], keep[P]; equals the quantised embedder's eval output bit for bit."""
+    x = fcontig(x)
+    if len(packed.tensors) != grid.n_levels or packed.rows != (1 << grid.log2_hashmap_size):
+        raise _lib.PocketNerfError("packed tables do not match the grid")
+    P = x.shape[0]
+    feat = torch.empty((P, 2 * grid.n_levels), dtype=torch.float32, device=x.device)
+    keep = torch.empty((P,), dtype=torch.bool, device=x.device)
+    with _guard(x):
+        if P > 0:
+            call("pn_hash_encode_fwd_packed", ctypes.byref(grid), ctypes.byref(packed.struct), dptr(x), P, dptr(feat),
+                 dptr(keep, torch.bool), stream())
+    return feat, keep
+
+
+def field_fwd_packed(grid, packed, w, pts, viewdirs, S, act_q=None):
+    """run_network on code tables in the bf16 tensor-core mode (one kernel, inference only) -> raw[P, 4|7]."""
+    pts, dirs = fcontig(pts), fcontig(viewdirs)
+    if grid.n_levels != 16 or len(packed.tensors) != 16 or packed.rows != (1 << grid.log2_hashmap_size):
+        raise _lib.PocketNerfError("the fused field kernel needs 16 packed levels matching the grid")
+    P = pts.shape[0]
+    C = 7 if w.get("n0w") is not None else 4
+    out = torch.empty((P, C), dtype=torch.float32, device=pts.device)
+    with _guard(pts):
+        if P > 0:
+            ws = _weights_struct(w)
+            call("pn_field_fwd_bf16_packed", ctypes.byref(grid), ctypes.byref(packed.struct), ctypes.byref(ws), dptr(pts),
+                 dptr(dirs), int(S), dptr(act_q, allow_none=True), P, dptr(out), None, stream())
+    return out

@@ -128,9 +128,40 @@ def read_quantized(path, device):
     return header, out
 
 
-def load_quantized(path, embed_fn, networks=None):
+def packed_levels_from_file(path, device, header=None):
+    """ops.PackedLevels built straight from the file's bit streams (u8 codes up to 8 bits, u16 up to 16, fp32 above):
+    what HashEmbedder gathers from in eval mode after load_quantized(..., packed=True)."""
+    with open(path, "rb") as f:
+        blob = f.read()
+    (hl,) = struct.unpack("<I", blob[4:8])
+    header = header or json.loads(blob[8:8 + hl].decode())
+    base = 8 + hl + ((-(8 + hl)) % 16)
+    levels = []
+    for m in header["tensors"]:
+        if not m["name"].startswith("embed_fn.embeddings."):
+            continue
+        raw = np.frombuffer(blob, dtype=np.uint8, count=m["nbytes"], offset=base + m["offset"])
+        n = int(np.prod(m["shape"]))
+        if m["storage"] == "packed":
+            words = torch.from_numpy(raw.view("<i4").copy()).to(device)
+            if m["bits"] <= 16:
+                t = ops.quant_unpack_codes(words, n, m["bits"], 1 if m["bits"] <= 8 else 2).reshape(m["shape"])
+            else:
+                scale = np.float32(m["scale"])
+                row = torch.tensor([scale, np.float32(scale + np.float32(1e-8)), m["zp"], m["qmin"], m["qmax"], 1, 0, 0],
+                                   dtype=torch.float32, device=device)
+                t = ops.quant_unpack(words, n, row, m["bits"]).reshape(m["shape"])
+            levels.append((t, m["scale"], m["zp"], m["qmin"]))
+        else:
+            levels.append((torch.from_numpy(raw.view("<f4").copy()).to(device).reshape(m["shape"]), 1.0, 0.0, 0.0))
+    return ops.PackedLevels(levels)
+
+
+def load_quantized(path, embed_fn, networks=None, packed=False):
     """Fill embed_fn / networks from a .pnq file.  Tables (and the first sigma weight) receive the dequantised
-    values and their quantisers are switched off, so eval-mode output equals the exporting model's."""
+    values and their quantisers are switched off, so eval-mode output equals the exporting model's.  With
+    packed=True the embedder additionally keeps the levels as integer codes and gathers from those in eval mode
+    (same output, 2-4 bytes per corner instead of 8)."""
     networks = networks or {}
     dev = embed_fn.embeddings[0].weight.device
     header, tensors = read_quantized(path, dev)
@@ -139,6 +170,9 @@ def load_quantized(path, embed_fn, networks=None):
             e.weight.copy_(tensors["embed_fn.embeddings.%d.weight" % l])
     if header["table_quantisation"]:
         embed_fn.use_quantization = False                   # hash_encoding.py:97 — values are already dequantised
+        if packed:
+            embed_fn.eval()
+            embed_fn.set_packed(packed_levels_from_file(path, dev, header))
     for prefix, net in networks.items():
         sd = {k[len(prefix) + 1:]: v for k, v in tensors.items() if k.startswith(prefix + ".")}
         packed_w0 = any(m["name"] == prefix + ".sigma_net.0.weight" and m["storage"] == "packed" for m in header["tensors"])

@@ -34,8 +34,18 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
         if not embed_fn._is_flat():
             embed_fn._reflatten()
         pts = inputs.reshape(-1, 3)
-        qrows = embed_fn._quant_rows(pts.detach())
         keys, weights = fn.kernel_weights()
+        if embed_fn._packed is not None and not embed_fn.training and not fn.training:
+            # inference from tables held as integer codes (HashEmbedder.pack_for_inference): no autograd
+            w = {k: ops.fcontig(t.detach()) for k, t in zip(keys, weights)}
+            act_q = fn.act_qrow(None, weights[0])
+            if ops.get_mlp_mode() == "bf16" and embed_fn.n_levels == 16:
+                out = ops.field_fwd_packed(embed_fn.grid(), embed_fn._packed, w, pts.detach(), viewdirs, S, act_q)
+            else:
+                feat, keep = ops.hash_encode_fwd_packed(embed_fn.grid(), embed_fn._packed, pts.detach())
+                out = ops.mlp_fwd(w, feat, dirs=ops.fcontig(viewdirs), samples_per_ray=S, act_q=act_q, keep=keep)
+            return out.reshape(N, S, out.shape[-1])
+        qrows = embed_fn._quant_rows(pts.detach())
         act_q = None
         if fn.use_quantization and fn.sigma_act_quantizers is not None:
             feat0 = None

@@ -166,4 +166,50 @@ double emu_ssim_sum(const float *a, const float *b, int H, int W, int C, double 
   return tot;
 }
 
+void emu_quant_codes(const float *x, int64_t n, const float *qrow, int code_bytes, void *out) {
+  for (int64_t k = 0; k < n; ++k) {
+    const uint32_t c = quant_code(x[k], qrow[1], qrow[2], qrow[3], qrow[4]);
+    if (code_bytes == 1) ((uint8_t *)out)[k] = (uint8_t)c; else ((uint16_t *)out)[k] = (uint16_t)c;
+  }
+}
+
+void emu_quant_unpack_codes(const uint32_t *words, int64_t n, int bits, int code_bytes, void *out) {
+  for (int64_t k = 0; k < n; ++k) {
+    const uint32_t c = unpack_one(words + (k >> 5) * bits, (int)(k & 31), bits);
+    if (code_bytes == 1) ((uint8_t *)out)[k] = (uint8_t)c; else ((uint16_t *)out)[k] = (uint16_t)c;
+  }
+}
+
+// hash_fwd_packed_kernel's per-point arithmetic: entries read as little-endian code pairs, decoded, interpolated
+void emu_hash_encode_packed(const pn_hash_grid *grid, const pn_packed_tables *pk, const float *x, int64_t P, float *feat,
+                            uint8_t *keep) {
+  const HashGridDev G = make_grid_dev(*grid);
+  const int L = G.n_levels;
+  PackedDev T;
+  for (int l = 0; l < L; ++l) {
+    T.t[l] = pk->codes[l]; T.eb[l] = (uint8_t)pk->entry_bytes[l];
+    T.scale[l] = pk->scale[l]; T.sub[l] = packed_sub_const(pk->zero_point[l], pk->qmin[l]);
+  }
+  for (int64_t p = 0; p < P; ++p) {
+    const float xv[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+    for (int l = 0; l < L; ++l) {
+      Cell c;
+      point_cell(G, l, xv, c);
+      float e0[8], e1[8];
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t h = corner_index(G, c, k);
+        if (T.eb[l] == 2) packed_decode(T, l, ((const uint16_t *)T.t[l])[h], false, e0[k], e1[k]);
+        else if (T.eb[l] == 4) packed_decode(T, l, ((const uint32_t *)T.t[l])[h], true, e0[k], e1[k]);
+        else {
+          e0[k] = ((const float *)T.t[l])[2 * h];
+          e1[k] = ((const float *)T.t[l])[2 * h + 1];
+        }
+      }
+      feat[p * 2 * L + 2 * l] = trilerp(e0, c.w);
+      feat[p * 2 * L + 2 * l + 1] = trilerp(e1, c.w);
+    }
+    if (keep) keep[p] = point_keep(G, xv) ? 1 : 0;
+  }
+}
+
 }  // extern "C"

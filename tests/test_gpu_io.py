@@ -251,3 +251,109 @@ def test_quant_pack_full_size_table_properties(pn):
         assert torch.equal(y, q(x))
     codes = torch.round(y / row[0] + row[2])                      # exact lattice: (q - zp)*scale / scale + zp
     assert codes.min() >= 0 and codes.max() <= 63 and 62 <= torch.unique(codes).numel() <= 64
+
+
+# ---- tables resident as integer codes ----------------------------------------------------------------------------------------
+def test_packed_gather_kernel_matches_reference_eval_golden(pn, golden):
+    """hash_fwd_packed_kernel on u8 codes == the live reference's quantised embedder in eval mode, bit for bit."""
+    from oracle.fixtures import synthetic_tables
+    g = golden("hash_embed_quant_eval")
+    tables = [cu(t) for t in synthetic_tables(16, 15, salt=5)]
+    x = cu(g["x"])
+    res = [float(r) for r in O.level_resolutions(16, 512)]
+    grid = pn.ops.make_grid(g["box_min"].tolist(), g["box_max"].tolist(), res, 15)
+    for force_bits in (None, 12.0, 20.0):
+        levels, rows = [], []
+        for l in range(16):
+            st = g["q%d" % l]
+            soft = float(st[0]) if force_bits is None else force_bits
+            bits, scale, zp, qmin, qmax = D.lbq_eval_params(soft, st[1], st[2], False)
+            row = torch.tensor([scale, np.float32(scale + np.float32(1e-8)), zp, qmin, qmax, 1, 0, 0], dtype=torch.float32, device="cuda")
+            rows.append(row)
+            if bits <= 16:
+                t = pn.ops.quant_codes(tables[l], row, 1 if bits <= 8 else 2)
+                want = D.quant_codes(tables[l].cpu().numpy().reshape(-1), scale, zp, qmin, qmax)
+                got = t.cpu().numpy().reshape(-1)
+                assert np.array_equal(got.view(np.uint8 if bits <= 8 else np.uint16).astype(np.int64), want)
+                words = pn.ops.quant_pack(tables[l], row, bits)
+                assert torch.equal(pn.ops.quant_unpack_codes(words, tables[l].numel(), bits, 1 if bits <= 8 else 2).reshape(t.shape), t)
+            else:
+                words = pn.ops.quant_pack(tables[l], row, bits)
+                t = pn.ops.quant_unpack(words, tables[l].numel(), row, bits).reshape(tables[l].shape)
+            levels.append((t, scale, zp, qmin))
+        packed = pn.ops.PackedLevels(levels)
+        feat, keep = pn.ops.hash_encode_fwd_packed(grid, packed, x)
+        if force_bits is None:
+            assert np.array_equal(feat.cpu().numpy(), g["feat"])
+        feat_fq, keep_fq = pn.ops.hash_encode_fwd(grid, tables, x, torch.stack(rows).contiguous())
+        assert torch.equal(feat, feat_fq) and torch.equal(keep, keep_fq)
+        assert packed.nbytes() < sum(t.numel() * 4 for t in tables) or force_bits == 20.0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_packed_inference_renders_identically(pn, tmp_path, mode):
+    """Eval-mode fake-quantised model == the same model gathering from integer codes (pack_for_inference) == the model
+    loaded from its .pnq export with packed=True: identical embeddings and frames, in both arithmetic modes."""
+    from indoor_nerf_b200 import quant_export
+    sc, _, kw = small_model(pn, use_quantization=True)
+    emb, nets = kw["embed_fn"], [kw["network_fn"], kw["network_fine"]]
+    bits = [3.0, 4.2, 5.0, 6.0, 6.6, 7.0, 8.0, 8.0, 9.0, 10.0, 11.3, 12.0, 14.0, 16.0, 20.0, 26.0]
+    x = (torch.rand(4096, 3, device="cuda") - 0.5) * 2.5
+    for l, q in enumerate(emb.quantizers):
+        q.calibrate(emb.embeddings[l].weight.detach())
+        q.soft_bits.data.fill_(bits[l])
+    emb.eval()
+    for n in nets:
+        n.sigma_weight_quantizer.calibrate(n.sigma_net[0].weight.detach())
+        # a calibration range that straddles zero: with the reference's own calibration (min of a ReLU output = 0) the
+        # zero point equals qmax and every hidden activation quantises to 0 (SURVEY section 8a6 quirk), which would make
+        # the frames independent of the tables and this comparison vacuous
+        n.sigma_act_quantizers[0].calibrate(torch.tensor([-0.5, 0.5], device="cuda"))
+        n.eval()
+    c2w = torch.from_numpy(sc["poses"][0][:3, :4]).cuda()
+
+    def same_frame(a, b, what):
+        if mode == "fp32":
+            assert torch.equal(a, b), what
+        else:
+            # bf16 mode: the packed gather interpolates in the code domain and scales once; the fake-quant gather
+            # multiplies by a reciprocal — both within fp32 rounding of the exact form before the bf16 rounding
+            # (a ray whose last sample has sigma ~ 0 sits on raw2outputs' 1e10-interval discontinuity: allow 3 outliers)
+            d = (a - b).abs()
+            assert int((d > 2e-3).sum()) <= 3 and d.median().item() < 2e-5, (what, d.max().item(), d.median().item())
+
+    with torch.no_grad():
+        frame_exact = pn.render(sc["H"], sc["W"], sc["K"], chunk=512, c2w=c2w, **kw)[0]      # fp32 mode, fake-quant in the gather
+    pn.set_mlp_mode(mode)
+    try:
+        with torch.no_grad():
+            feat_q, keep_q = emb(x)
+            frame_q = pn.render(sc["H"], sc["W"], sc["K"], chunk=512, c2w=c2w, **kw)[0]
+            packed = emb.pack_for_inference()
+            assert [t.dtype for t in packed.tensors] == [torch.uint8] * 8 + [torch.int16] * 6 + [torch.float32] * 2
+            feat_p, keep_p = emb(x)
+            frame_p = pn.render(sc["H"], sc["W"], sc["K"], chunk=512, c2w=c2w, **kw)[0]
+        assert torch.equal(feat_p, feat_q) and torch.equal(keep_p, keep_q)
+        same_frame(frame_p, frame_q, "codes vs fake-quant")
+        if mode == "bf16":                                            # and both sit within the bf16 mode's bar of the exact frame
+            for f in (frame_p, frame_q):
+                assert (f - frame_exact).abs().median().item() < 2e-3
+        emb.train()
+        assert emb._packed is None                                   # the snapshot does not survive training
+        emb.eval()
+        path = str(tmp_path / "m.pnq")
+        quant_export.export_quantized(path, emb, {"network_fn": nets[0], "network_fine": nets[1]})
+        sc2, _, kw2 = small_model(pn, use_quantization=True)
+        emb2, nets2 = kw2["embed_fn"], [kw2["network_fn"], kw2["network_fine"]]
+        quant_export.load_quantized(path, emb2, {"network_fn": nets2[0], "network_fine": nets2[1]}, packed=True)
+        [n.eval() for n in nets2]
+        assert emb2._packed is not None and not emb2.training
+        with torch.no_grad():
+            feat_l, _ = emb2(x)
+            frame_l = pn.render(sc["H"], sc["W"], sc["K"], chunk=512, c2w=c2w, **kw2)[0]
+        assert torch.equal(feat_l, feat_q)
+        same_frame(frame_l, frame_p, "loaded codes vs packed")
+        if mode == "fp32":
+            assert torch.equal(frame_l, frame_q)
+    finally:
+        pn.set_mlp_mode("fp32")

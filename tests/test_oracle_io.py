@@ -125,3 +125,63 @@ def test_quant_codes_roundtrip(emu, golden, tag, k, sym, src):
     y = np.zeros_like(x)
     emu.emu_quant_unpack(ptr(w2), ctypes.c_int64(x.size), ptr(row), bits, ptr(y))
     assert (y == g[pre + "out"]).all()
+
+
+# ---- tables resident as integer codes: the gather must reproduce the reference's eval-mode quantised embedder -------------
+class _Grid(ctypes.Structure):
+    _fields_ = [("box_min", ctypes.c_float * 3), ("box_max", ctypes.c_float * 3), ("resolution", ctypes.c_float * 16),
+                ("n_levels", ctypes.c_int32), ("log2_hashmap_size", ctypes.c_int32)]
+
+
+class _Packed(ctypes.Structure):
+    _fields_ = [("codes", ctypes.c_void_p * 16), ("entry_bytes", ctypes.c_int32 * 16), ("scale", ctypes.c_float * 16),
+                ("zero_point", ctypes.c_float * 16), ("qmin", ctypes.c_float * 16)]
+
+
+@pytest.mark.parametrize("force_bits", [None, 12.0, 20.0])
+def test_hostemu_packed_gather_matches_reference_eval(emu, golden, force_bits):
+    import torch
+    from oracle import hashnerf_oracle as O
+    from oracle.fixtures import synthetic_tables
+    g = golden("hash_embed_quant_eval")
+    tables = [np.ascontiguousarray(t) for t in synthetic_tables(16, 15, salt=5)]
+    x = np.ascontiguousarray(g["x"])
+    P = x.shape[0]
+    grid = _Grid()
+    grid.box_min[:] = list(g["box_min"]); grid.box_max[:] = list(g["box_max"])
+    grid.resolution[:] = [float(r) for r in O.level_resolutions(16, 512)]
+    grid.n_levels, grid.log2_hashmap_size = 16, 15
+    pk, keepalive, rows = _Packed(), [], np.zeros((16, 8), np.float32)
+    for l in range(16):
+        st = g["q%d" % l]
+        soft = float(st[0]) if force_bits is None else force_bits
+        bits, scale, zp, qmin, qmax = D.lbq_eval_params(soft, st[1], st[2], False)
+        rows[l] = qrow_of(scale, zp, qmin, qmax)
+        if bits <= 16:
+            cb = 1 if bits <= 8 else 2
+            codes = np.zeros(tables[l].size, np.uint8 if cb == 1 else np.uint16)
+            emu.emu_quant_codes(ptr(tables[l]), ctypes.c_int64(tables[l].size), ptr(rows[l]), cb, ptr(codes))
+            assert (codes.astype(np.int64) == D.quant_codes(tables[l].reshape(-1), scale, zp, qmin, qmax)).all()
+            # the same codes out of the bit stream
+            words = D.pack_bits(codes, bits)
+            c2 = np.zeros_like(codes)
+            emu.emu_quant_unpack_codes(ptr(words), ctypes.c_int64(codes.size), bits, cb, ptr(c2))
+            assert (c2 == codes).all()
+            pk.entry_bytes[l] = 2 * cb
+        else:
+            codes = D.dequant_codes(D.quant_codes(tables[l].reshape(-1), scale, zp, qmin, qmax), scale, zp, qmin)
+            pk.entry_bytes[l] = 8
+        keepalive.append(codes)
+        pk.codes[l] = codes.ctypes.data
+        pk.scale[l], pk.zero_point[l], pk.qmin[l] = scale, zp, qmin
+    feat = np.zeros((P, 32), np.float32)
+    keep = np.zeros(P, np.uint8)
+    emu.emu_hash_encode_packed(ctypes.byref(grid), ctypes.byref(pk), ptr(x), ctypes.c_int64(P), ptr(feat), ptr(keep))
+    if force_bits is None:
+        assert (feat == g["feat"]).all()                    # the live reference's eval-mode output, bit for bit
+    # and always: equal to fake-quantising the fp32 entries in the gather (the training-time kernel in eval form)
+    rows[:, 5] = 1.0
+    feat_fq = np.zeros((P, 32), np.float32)
+    tp = (ctypes.c_void_p * 16)(*[t.ctypes.data for t in tables])
+    emu.emu_hash_encode(ctypes.byref(grid), tp, ptr(rows), ptr(x), ctypes.c_int64(P), ptr(feat_fq), None, None)
+    assert (feat == feat_fq).all()
