@@ -227,8 +227,7 @@ hash_fwd_packed_kernel(const __grid_constant__ HashGridDev G, const __grid_const
       Cell c;
       point_cell(G, l, xv, c);
       float e0[8], e1[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) packed_entry<true>(T, l, corner_index(G, c, k), e0[k], e1[k]);
+packed_gather8<true>(T, l, G, c, e0, e1);
       st[lane * kStagePitch + 2 * l + 0] = trilerp(e0, c.w);
       st[lane * kStagePitch + 2 * l + 1] = trilerp(e1, c.w);
     }

@@ -131,26 +131,42 @@ PN_HD void packed_decode(const PackedDev &T, int l, uint32_t word, bool u16, flo
 }
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ uint32_t packed_word(const PackedDev &T, int l, uint32_t h, bool u16) {
-  return u16 ? __ldg(reinterpret_cast<const uint32_t *>(T.t[l]) + h)
-             : (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(T.t[l]) + h);
-}
-
+// The 8 corner entries of one level.  The format branch is taken once per level (uniform across the grid) and, inside
+// it, all 8 loads are issued before the first decode touches a loaded word, so the gathers overlap exactly as in the
+// fp32 kernels (a per-corner branch made each decode wait for its own load: 8 serialised L2 round trips per level).
 // EXACT = true : e = (q - zp) * scale per gathered value (fp32 path, bit-exact with the fake-quantised fp32 entry).
 // EXACT = false: e = q - zp; the caller interpolates in the code domain and multiplies the result by scale once
 //                (bf16 path: 16 multiplies per level become 2; differs from EXACT by fp32 rounding only).
 template <bool EXACT>
-__device__ __forceinline__ void packed_entry(const PackedDev &T, int l, uint32_t h, float &e0, float &e1) {
+__device__ __forceinline__ void packed_gather8(const PackedDev &T, int l, const HashGridDev &G, const Cell &c, float e0[8],
+                                               float e1[8]) {
   const int eb = T.eb[l];
   if (eb == 8) {
-    const float2 e = __ldg(reinterpret_cast<const float2 *>(T.t[l]) + h);
-    e0 = e.x;
-    e1 = e.y;
+    const float2 *__restrict__ tab = reinterpret_cast<const float2 *>(T.t[l]);
+    float2 e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = __ldg(tab + corner_index(G, c, k));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { e0[k] = e[k].x; e1[k] = e[k].y; }
     return;
   }
-  const uint32_t w = packed_word(T, l, h, eb == 4);
-  if (EXACT) packed_decode(T, l, w, eb == 4, e0, e1);
-  else packed_levels_q(w, eb == 4, T.sub[l], e0, e1);
+  uint32_t w[8];
+  if (eb == 4) {
+    const uint32_t *__restrict__ tab = reinterpret_cast<const uint32_t *>(T.t[l]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __ldg(tab + corner_index(G, c, k));
+  } else {
+    const uint16_t *__restrict__ tab = reinterpret_cast<const uint16_t *>(T.t[l]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __ldg(tab + corner_index(G, c, k));
+  }
+  const bool u16 = eb == 4;
+  const float sub = T.sub[l], scale = T.scale[l];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    packed_levels_q(w[k], u16, sub, e0[k], e1[k]);
+    if (EXACT) { e0[k] = pn_mul(e0[k], scale); e1[k] = pn_mul(e1[k], scale); }
+  }
 }
 #endif
 

@@ -236,8 +236,7 @@ __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, con
         point_cell<false>(F->G, l, xv, c);
         float e0[8], e1[8];
         if (SRC == SRC_PACKED) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) packed_entry<false>(F->PK, l, corner_index(F->G, c, k), e0[k], e1[k]);
+packed_gather8<false>(F->PK, l, F->G, c, e0, e1);
         } else {
           const float2 *__restrict__ tab = F->T.t[l];
 #pragma unroll
