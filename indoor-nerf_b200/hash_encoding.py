@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .quantization import LearnedBitwidthQuantizer
+from .quantization import LearnedBitwidthQuantizer, qrows_batched
 
 
 class TableLevel(nn.Embedding):
@@ -122,7 +122,7 @@ class HashEmbedder(nn.Module):
             for l, q in enumerate(self.quantizers):
                 if not q.calibrated:
                     q.calibrate_minmax(mm[l, 0], mm[l, 1])
-        return torch.stack([q.qrow(self.training) for q in self.quantizers]).contiguous()
+        return qrows_batched(list(self.quantizers), self.training).contiguous()
 
     # -- tables as integer codes (inference) ----------------------------------------------------------------------
     def pack_for_inference(self):

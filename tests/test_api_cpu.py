@@ -235,3 +235,23 @@ def test_patch_installs_renderer_into_live_reference():
     finally:
         for n, fn in saved.items():
             setattr(ref.run_nerf, n, fn)
+
+
+def test_batched_quantiser_rows_equal_the_per_quantiser_rows():
+    """hash_encoding._quant_rows builds all levels' kernel rows with vectorised ops; they must equal the rows each
+    LearnedBitwidthQuantizer computes for itself (quantization.py:121-175), bit for bit, in both forms."""
+    from indoor_nerf_b200.quantization import qrows_batched
+    torch.manual_seed(3)
+    for symmetric in (False, True):
+        qs = []
+        for l in range(16):
+            q = pn.LearnedBitwidthQuantizer(init_bits=8.0, min_bits=2.0, max_bits=32.0, symmetric=symmetric)
+            q.calibrate(torch.randn(1000) * (10.0 ** (-l / 3.0)))
+            q.soft_bits.data.fill_(float(torch.empty(()).uniform_(1.0, 33.0)))
+            qs.append(q)
+        for training in (True, False):
+            want = torch.stack([q.qrow(training) for q in qs])
+            got = qrows_batched(qs, training)
+            assert got.shape == (16, 8) and torch.equal(got, want), (symmetric, training)
+    mixed = [pn.LearnedBitwidthQuantizer(symmetric=True), pn.LearnedBitwidthQuantizer(symmetric=False)]
+    assert torch.equal(qrows_batched(mixed, False), torch.stack([q.qrow(False) for q in mixed]))
