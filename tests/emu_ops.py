@@ -15,14 +15,29 @@ EMU_DIR = os.path.join(HERE, "hostemu")
 _lib = None
 
 
+def build():
+    """Compile tests/hostemu/hostemu.cpp if the .so is missing or older than its sources.  Written to a private
+    temporary file and renamed into place, so concurrent callers (two gloo ranks, xdist workers) never load a
+    half-written library."""
+    import glob
+    so = os.path.join(EMU_DIR, "libhostemu.so")
+    csrc = os.path.join(os.path.dirname(HERE), "indoor-nerf_b200", "csrc")
+    srcs = [os.path.join(EMU_DIR, "hostemu.cpp"), os.path.join(os.path.dirname(HERE), "include", "pocketnerf.h")] + \
+        glob.glob(os.path.join(csrc, "*.cuh"))
+    if os.path.isfile(so) and os.path.getmtime(so) >= max(os.path.getmtime(f) for f in srcs):
+        return so
+    tmp = "%s.%d.tmp" % (so, os.getpid())
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17",
+                           "-I/usr/local/cuda/include", "-Wno-unknown-pragmas", "-o", tmp,
+                           os.path.join(EMU_DIR, "hostemu.cpp")])
+    os.replace(tmp, so)
+    return so
+
+
 def lib():
     global _lib
     if _lib is None:
-        so = os.path.join(EMU_DIR, "libhostemu.so")
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17",
-                               "-I/usr/local/cuda/include", "-Wno-unknown-pragmas", "-o", so,
-                               os.path.join(EMU_DIR, "hostemu.cpp")])
-        _lib = ctypes.CDLL(so)
+        _lib = ctypes.CDLL(build())
         _lib.emu_ssim_sum.restype = ctypes.c_double
     return _lib
 

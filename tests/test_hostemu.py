@@ -25,10 +25,8 @@ class Grid(ctypes.Structure):
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(EMU_DIR, "libhostemu.so")
-    src = os.path.join(EMU_DIR, "hostemu.cpp")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17",
-                           "-I/usr/local/cuda/include", "-Wno-unknown-pragmas", "-o", so, src])
+    from tests import emu_ops
+    so = emu_ops.build()
     return ctypes.CDLL(so)
 
 

@@ -17,10 +17,8 @@ QROW = 8
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(EMU_DIR, "libhostemu.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17",
-                           "-I/usr/local/cuda/include", "-Wno-unknown-pragmas", "-o", so,
-                           os.path.join(EMU_DIR, "hostemu.cpp")])
+    from tests import emu_ops
+    so = emu_ops.build()
     lib = ctypes.CDLL(so)
     lib.emu_ssim_sum.restype = ctypes.c_double
     return lib

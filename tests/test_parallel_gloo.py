@@ -110,6 +110,44 @@ def _broadcast_and_calibration(rank, world):
     return ok
 
 
+def _ray_bank_ranks(rank, world):
+    """RayBank with a process group: rank-divergent RNG states must not matter (rank 0's permutation is broadcast at
+    every shuffle / epoch roll-over) and the ranks' shards must tile the global batch."""
+    import numpy as np
+    from indoor_nerf_b200 import ops, ray_bank
+    from tests import emu_ops
+    ops.ray_bank_batch = emu_ops.ray_bank_batch                 # host build of the kernel's arithmetic (no GPU here)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ray_bank.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    bank = ray_bank.RayBank(H, W, g["K"], g["poses"], g["images"], [int(i) for i in g["i_train"]], device="cpu",
+                            group=dist.group.WORLD)
+    np.random.seed(0 if rank == 0 else 1234)                    # only rank 0's draws may count
+    torch.manual_seed(7 + 100 * rank)
+    bank.shuffle()
+    out = []
+    for it in range(5):                                         # 140 rays, batches of 48: rolls over after the third
+        rays, tgt = bank.next_batch(48)
+        out.append((rays.numpy(), tgt.numpy(), bank.order.numpy().copy()))
+    return out
+
+
+def test_ray_bank_shards_and_permutation_sync():
+    import numpy as np
+    res = _run("_ray_bank_ranks")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ray_bank.npz"))
+    ref = g["shuffled"]                                         # np.random.seed(0) shuffle = rank 0's permutation
+    i_batch = 0
+    for it in range(5):
+        (r0, t0, o0), (r1, t1, o1) = res[0][it], res[1][it]
+        assert (o0 == o1).all()                                 # same permutation on both ranks after every call
+        rays, tgt = np.concatenate([r0, r1], 1), np.concatenate([t0, t1], 0)
+        if it < 3:                                              # first epoch: comparable with the reference's bank
+            want = ref[i_batch:i_batch + 48]
+            assert (rays[0] == want[:, 0]).all() and (rays[1] == want[:, 1]).all() and (tgt == want[:, 2]).all()
+            i_batch += 48
+        assert abs(r0.shape[1] - r1.shape[1]) <= 1 and rays.shape[1] in (48, 44)
+
+
 def test_allreduce_gradients():
     assert all(_run("_allreduce"))
 
