@@ -68,6 +68,7 @@ class HashEmbedder(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         self._reflatten()
+        self._packed = None                                       # a code snapshot does not follow .to() / .float()
         return out
 
     def _is_flat(self):

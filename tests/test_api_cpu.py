@@ -255,3 +255,29 @@ def test_batched_quantiser_rows_equal_the_per_quantiser_rows():
             assert got.shape == (16, 8) and torch.equal(got, want), (symmetric, training)
     mixed = [pn.LearnedBitwidthQuantizer(symmetric=True), pn.LearnedBitwidthQuantizer(symmetric=False)]
     assert torch.equal(qrows_batched(mixed, False), torch.stack([q.qrow(False) for q in mixed]))
+
+
+def test_png_writer_roundtrip(tmp_path):
+    """render_path saves plain PNGs (8-bit RGB / gray, one IDAT chunk, filter 0): decode by hand and compare."""
+    import struct
+    import zlib
+    from indoor_nerf_b200.render import _write_png
+    rs = np.random.RandomState(0)
+    for shape in ((5, 7, 3), (9, 4)):
+        img = rs.randint(0, 256, shape).astype(np.uint8)
+        path = str(tmp_path / ("x%d.png" % len(shape)))
+        _write_png(path, img)
+        raw = open(path, "rb").read()
+        assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+        w, h, depth, color = struct.unpack(">IIBB", raw[16:26])
+        assert (h, w, depth, color) == (shape[0], shape[1], 8, 2 if len(shape) == 3 else 0)
+        pos, chunks = 8, {}
+        while pos < len(raw):
+            n, tag = struct.unpack(">I", raw[pos:pos + 4])[0], raw[pos + 4:pos + 8]
+            data = raw[pos + 8:pos + 8 + n]
+            assert struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0] == (zlib.crc32(tag + data) & 0xffffffff)
+            chunks[tag] = data
+            pos += 12 + n
+        assert set(chunks) == {b"IHDR", b"IDAT", b"IEND"}
+        rows = np.frombuffer(zlib.decompress(chunks[b"IDAT"]), np.uint8).reshape(shape[0], -1)
+        assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(shape), img)
