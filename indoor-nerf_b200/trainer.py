@@ -47,4 +47,16 @@ class Trainer:
         self.step_idx += 1
         if self.step_idx > 1000:                                   # run_nerf.py:1036-1037
             self.tv_weight = 0.0
+        self.decay_learning_rate()
         return loss.detach(), mse2psnr(img_loss.detach())
+
+    def decay_learning_rate(self):
+        """run_nerf.py:1289-1293: lr = lrate * 0.1 ** (global_step / (lrate_decay * 1000)) on every group (a host scalar;
+        RAdam folds it into its fused update).  The reference evaluates this before `global_step += 1` (:1475), i.e.
+        with the number of iterations completed BEFORE the current one."""
+        decay = getattr(self.args, "lrate_decay", None)
+        if not decay:
+            return
+        new_lrate = self.args.lrate * (0.1 ** ((self.step_idx - 1) / (decay * 1000)))
+        for g in self.opt.param_groups:
+            g["lr"] = new_lrate

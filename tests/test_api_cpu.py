@@ -281,3 +281,22 @@ def test_png_writer_roundtrip(tmp_path):
         assert set(chunks) == {b"IHDR", b"IDAT", b"IEND"}
         rows = np.frombuffer(zlib.decompress(chunks[b"IDAT"]), np.uint8).reshape(shape[0], -1)
         assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(shape), img)
+
+
+def test_trainer_learning_rate_schedule():
+    """Trainer.decay_learning_rate follows run_nerf.py:1289-1293 (evaluated before global_step += 1 at :1475)."""
+    from types import SimpleNamespace
+    from indoor_nerf_b200.trainer import Trainer
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = pradam.RAdam([{"params": [p], "weight_decay": 1e-6}, {"params": [torch.nn.Parameter(torch.zeros(2))], "eps": 1e-15}],
+                       lr=0.01, betas=(0.9, 0.99))
+    tr = Trainer.__new__(Trainer)
+    tr.args, tr.opt, tr.step_idx = SimpleNamespace(lrate=0.01, lrate_decay=10), opt, 0
+    for step in (1, 500, 10000):
+        tr.step_idx = step
+        tr.decay_learning_rate()
+        want = 0.01 * (0.1 ** ((step - 1) / 10000))
+        assert all(g["lr"] == want for g in opt.param_groups)
+    tr.args = SimpleNamespace(lrate=0.01)
+    tr.decay_learning_rate()                                      # no lrate_decay: left alone
+    assert opt.param_groups[0]["lr"] == 0.01 * (0.1 ** (9999 / 10000))
