@@ -175,3 +175,50 @@ def test_pnq_unquantised_model_is_stored_fp32(emu_kernels, tmp_path):
     with pytest.raises(ValueError):
         open(path, "r+b").write(b"XXXX")
         quant_export.read_quantized(path, "cpu")
+
+
+def test_ray_bank_edge_cases(emu_kernels, golden):
+    H, W, K, poses, images, i_train, g = scene(golden)
+    bank = ray_bank.RayBank(H, W, K, poses, images, i_train, device="cpu")
+    np.random.seed(0)
+    bank.shuffle()
+    # a batch larger than the bank: the reference's slice is simply short, and the epoch rolls over
+    torch.manual_seed(0)
+    rays, tgt = bank.next_batch(1000)
+    assert rays.shape == (2, 140, 3) and tgt.shape == (140, 3) and bank.i_batch == 0
+    assert (rays.numpy()[1] == g["shuffled"][:, 1]).all()
+    # more ranks than rays in the (short) batch: some shards are empty, the rest still tile it
+    np.random.seed(0)
+    parts = []
+    for r in range(8):
+        b = ray_bank.RayBank(H, W, K, poses, images, i_train, device="cpu")
+        np.random.seed(0)
+        b.shuffle()
+        b.rank, b.world, b._sync_order = r, 8, (lambda: None)
+        parts.append(b.next_batch(5)[0])
+    assert sorted(p.shape[1] for p in parts) == [0, 0, 0, 1, 1, 1, 1, 1]
+    assert (torch.cat(parts, 1).numpy()[1] == g["shuffled"][:5, 1]).all()
+    # images must already be RGB
+    with pytest.raises(ValueError):
+        ray_bank.RayBank(H, W, K, poses, np.zeros((5, H, W, 4), np.float32), i_train, device="cpu")
+
+
+def test_pnq_tensor_not_multiple_of_32_is_stored_fp32(emu_kernels, tmp_path):
+    """A level whose element count is not a multiple of 32 cannot be bit-packed in 32-value groups: it is stored as the
+    eval fake-quantised fp32 values instead, and still loads to exactly those values."""
+    box = (torch.tensor([-1.0] * 3), torch.tensor([1.0] * 3))
+    emb = pn.HashEmbedder(box, log2_hashmap_size=3, use_quantization=True)          # 8 rows x 2 = 16 values per level
+    with torch.no_grad():
+        emb.table_storage.mul_(100.0)
+    for l, q in enumerate(emb.quantizers):
+        q.calibrate(emb.embeddings[l].weight.detach())
+    emb.eval()
+    with torch.no_grad():
+        want = [emb.quantizers[l](emb.embeddings[l].weight) for l in range(16)]
+    path = str(tmp_path / "tiny.pnq")
+    header = quant_export.export_quantized(path, emb)
+    assert header["table_quantisation"] and all(m["storage"] == "fp32" for m in header["tensors"])
+    emb2 = pn.HashEmbedder(box, log2_hashmap_size=3, use_quantization=True)
+    quant_export.load_quantized(path, emb2)
+    assert all(torch.equal(emb2.embeddings[l].weight.detach(), want[l]) for l in range(16))
+    assert emb2.use_quantization is False

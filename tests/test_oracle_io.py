@@ -183,3 +183,34 @@ def test_hostemu_packed_gather_matches_reference_eval(emu, golden, force_bits):
     tp = (ctypes.c_void_p * 16)(*[t.ctypes.data for t in tables])
     emu.emu_hash_encode(ctypes.byref(grid), tp, ptr(rows), ptr(x), ctypes.c_int64(P), ptr(feat_fq), None, None)
     assert (feat == feat_fq).all()
+
+
+@pytest.mark.parametrize("bits", list(range(1, 25)))
+def test_pack_unpack_every_width(emu, bits):
+    """Bit stream round trip at every width the exporter can emit (1..24), asymmetric and symmetric ranges, with the
+    extreme codes 0 and 2^bits-1 present: host build of the kernels' arithmetic == numpy oracle == input codes."""
+    rs = np.random.RandomState(bits)
+    n = 32 * 37
+    for sym in (False, True):
+        qmin = np.float32(-(2 ** (bits - 1)) if sym else 0)
+        qmax = np.float32(2 ** (bits - 1) - 1 if sym else 2 ** bits - 1)
+        zp = np.float32(0 if sym else rs.randint(0, 2 ** bits))
+        scale = np.float32(rs.uniform(1e-7, 1e-2))
+        codes = rs.randint(0, 2 ** bits, n).astype(np.int64)
+        codes[:2] = [0, 2 ** bits - 1]
+        x = D.dequant_codes(codes, scale, zp, qmin)                       # values that sit exactly on the lattice
+        row = qrow_of(scale, zp, qmin, qmax)
+        # quantising lattice values may move them by a step (the reference's 1e-8 in the divisor): pack the oracle's codes
+        want_codes = D.quant_codes(x, scale, zp, qmin, qmax)
+        words = np.zeros(n * bits // 32, np.uint32)
+        emu.emu_quant_pack(ptr(x), ctypes.c_int64(n), ptr(row), bits, ptr(words))
+        assert (words == D.pack_bits(want_codes, bits)).all()
+        assert (D.unpack_bits(words, bits, n) == want_codes).all()
+        y = np.zeros(n, np.float32)
+        emu.emu_quant_unpack(ptr(words), ctypes.c_int64(n), ptr(row), bits, ptr(y))
+        assert (y == D.dequant_codes(want_codes, scale, zp, qmin)).all()
+        if bits <= 16:
+            cb = 1 if bits <= 8 else 2
+            c = np.zeros(n, np.uint8 if cb == 1 else np.uint16)
+            emu.emu_quant_unpack_codes(ptr(words), ctypes.c_int64(n), bits, cb, ptr(c))
+            assert (c.astype(np.int64) == want_codes).all()
