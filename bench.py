@@ -274,7 +274,7 @@ def io_legs(pn, scene, kw2, scene2, dev):
         out["ray_bank"] = {"error": repr(ex)}
     try:
         poses = torch.from_numpy(scene2["poses"][:3])
-        gts = torch.rand(3, 800, 800, 3)
+        gts = torch.rand(3, 800, 800, 3).pin_memory()          # ground truth as a loader would hold it: pinned host memory
         kw = dict(kw2, near=2., far=6.)
         hwf = [800, 800, scene2["focal"]]
         pn.render_path(poses[:1], hwf, scene2["K"], 1 << 17, kw, gt_imgs=gts[:1])
