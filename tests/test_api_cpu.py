@@ -300,3 +300,33 @@ def test_trainer_learning_rate_schedule():
     tr.args = SimpleNamespace(lrate=0.01)
     tr.decay_learning_rate()                                      # no lrate_decay: left alone
     assert opt.param_groups[0]["lr"] == 0.01 * (0.1 ** (9999 / 10000))
+
+
+def test_no_cpu_path_for_the_io_ops():
+    """The §8f entry points refuse host tensors like the rest of the path (no silent CPU fallback)."""
+    from indoor_nerf_b200 import ops
+    K = np.array([[10., 0, 2], [0, 10., 2], [0, 0, 1]])
+    ids = torch.arange(4)
+    with pytest.raises(_lib.PocketNerfError):
+        ops.ray_bank_batch(ids, 4, 4, K, torch.zeros(1, 3, 4), None, torch.zeros(1, 4, 4, 3))
+    with pytest.raises(_lib.PocketNerfError):
+        ops.image_sqerr(torch.zeros(8, 8, 3), torch.zeros(8, 8, 3))
+    with pytest.raises(_lib.PocketNerfError):
+        ops.image_ssim(torch.zeros(8, 8, 3), torch.zeros(8, 8, 3))
+    with pytest.raises(_lib.PocketNerfError):
+        ops.to8b(torch.zeros(8))
+    row = torch.tensor([1e-3, 1e-3, 0, 0, 255, 1, 0, 0])
+    with pytest.raises(_lib.PocketNerfError):
+        ops.quant_pack(torch.zeros(64), row, 8)
+    with pytest.raises(_lib.PocketNerfError):
+        ops.quant_codes(torch.zeros(64), row, 1)
+    with pytest.raises(_lib.PocketNerfError):
+        ops.PackedLevels([(torch.zeros(8, 2, dtype=torch.uint8), 1.0, 0.0, 0.0)])
+    emb = pn.HashEmbedder((torch.tensor([-1.0] * 3), torch.tensor([1.0] * 3)), log2_hashmap_size=5, use_quantization=True)
+    with pytest.raises(RuntimeError):
+        emb.pack_for_inference()                                     # quantisers not calibrated
+    # bad arguments are reported through the C ABI's error channel, without a device
+    lib = _lib.lib()
+    assert lib.pn_quant_pack(None, 64, None, 8, None, None) == -1 and b"NULL" in lib.pn_last_error()
+    assert lib.pn_image_ssim(None, None, 8, 8, 3, 1.0, None, None) == -1
+    assert lib.pn_quant_unpack_codes(None, 64, 9, 1, None, None) == -1
