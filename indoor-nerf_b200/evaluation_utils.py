@@ -66,7 +66,7 @@ class ComprehensiveEvaluator:
         with torch.no_grad():
             for pose, gt_img in zip(poses, images_gt):
                 c2w = torch.as_tensor(pose)[:3, :4]
-                if parallel.world_size(group) > 1:
+                if group is not None and parallel.world_size(group) > 1:
                     from .run_nerf_helpers import get_rays
                     ro, rd = get_rays(H, W, K, c2w)
                     rgb, _, _ = parallel.render_sharded(lambda h, w, **a: model_fn(h, w, K, chunk=chunk, **a), H, W,

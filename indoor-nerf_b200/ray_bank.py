@@ -38,8 +38,10 @@ class RayBank:
         self.images = img.to(self.device).contiguous()
         self.i_train = [int(i) for i in i_train]
         self.image_index = torch.tensor(self.i_train, dtype=torch.int32, device=self.device)
+        # group=None means "not distributed" here, even inside an initialised process group: a bank built by one rank
+        # alone (a benchmark leg, an evaluation script) must not start a collective the other ranks never join
         self.group = group
-        self.rank, self.world = parallel.rank(group), parallel.world_size(group)
+        self.rank, self.world = (parallel.rank(group), parallel.world_size(group)) if group is not None else (0, 1)
         self.order = None
         self.i_batch = 0
 

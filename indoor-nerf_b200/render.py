@@ -223,7 +223,9 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
     H, W = int(H), int(W)
     dev = torch.device("cuda", torch.cuda.current_device())
     n = len(render_poses)
-    world = parallel.world_size(group)
+    # group=None means "this process renders whole frames", even inside an initialised process group
+    world = parallel.world_size(group) if group is not None else 1
+    rank = parallel.rank(group) if group is not None else 0
     pin = dict(pin_memory=True)
     rgbs = torch.empty((n, H, W, 3), dtype=torch.float32, **pin)
     depths = torch.empty((n, H, W), dtype=torch.float32, **pin)
@@ -250,7 +252,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
                 rgb8s.append((ops.to8b(rgb).cpu(), ops.to8b(depth).cpu()))
     torch.cuda.synchronize(dev)
     rgbs, depths = rgbs.numpy(), depths.numpy()
-    if savedir is not None and parallel.rank(group) == 0:
+    if savedir is not None and rank == 0:
         os.makedirs(savedir, exist_ok=True)
         for i, (c8, d8) in enumerate(rgb8s):
             _write_png(os.path.join(savedir, "{:03d}.png".format(i)), c8.numpy())
@@ -259,7 +261,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
         psnrs = (-10. * torch.log10(sq / float(H * W * 3))).cpu().tolist()
         avg_psnr = sum(psnrs) / len(psnrs)
         print("Avg PSNR over Test set: ", avg_psnr)
-        if savedir is not None and parallel.rank(group) == 0:
+        if savedir is not None and rank == 0:
             with open(os.path.join(savedir, "test_psnrs_avg{:0.2f}.pkl".format(avg_psnr)), "wb") as fp:
                 pickle.dump(psnrs, fp)
         render_path.last_psnrs = psnrs

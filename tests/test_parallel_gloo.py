@@ -131,6 +131,37 @@ def _ray_bank_ranks(rank, world):
     return out
 
 
+def _group_none_is_local(rank, world):
+    """Inside an initialised process group, the §8f helpers called with group=None by ONE rank alone (bench.py's
+    rank-0 legs do exactly that) must not start a collective: they would deadlock against ranks that never join."""
+    import numpy as np
+    from indoor_nerf_b200 import ops, ray_bank
+    from tests import emu_ops
+    ok = True
+    if rank == 0:
+        ops.ray_bank_batch = emu_ops.ray_bank_batch
+        g = np.load(os.path.join(ROOT, "tests", "golden", "ray_bank.npz"))
+        bank = ray_bank.RayBank(int(g["H"]), int(g["W"]), g["K"], g["poses"], g["images"], [0, 2, 3, 4], device="cpu")
+        ok = bank.world == 1 and bank.rank == 0
+        np.random.seed(0)
+        bank.shuffle()
+        for _ in range(4):                                      # includes an epoch roll-over
+            rays, _ = bank.next_batch(48)
+        ok = ok and rays.shape[1] == 48
+    dist.barrier()
+    return ok
+
+
+def test_group_none_never_starts_a_collective():
+    assert all(_run("_group_none_is_local"))
+    import inspect
+    import indoor_nerf_b200 as pn
+    from indoor_nerf_b200 import evaluation_utils
+    # render_path / evaluate_test_set take the same precaution (they need a GPU to run, so the guard is checked in source)
+    assert "if group is not None else 1" in inspect.getsource(pn.render_path)
+    assert "group is not None and" in inspect.getsource(evaluation_utils.ComprehensiveEvaluator.evaluate_test_set)
+
+
 def test_ray_bank_shards_and_permutation_sync():
     import numpy as np
     res = _run("_ray_bank_ranks")
