@@ -75,7 +75,21 @@ PN_HD void point_cell(const HashGridDev &G, int level, const float x[3], Cell &c
     const float g = G.g[level][a];
     // torch.clamp(x, min, max) == min(max(x, lo), hi)
     const float xc = fminf(fmaxf(x[a], G.bmin[a]), G.bmax[a]);
-    const float fi = floorf(pn_div(pn_sub(xc, G.bmin[a]), g));
+    const float t = pn_sub(xc, G.bmin[a]);
+    float fi;
+    if (EXACT_W) {
+      fi = floorf(pn_div(t, g));
+    } else {
+      // The voxel index must be the reference's floor(RN(t / g)) bit for bit, but the IEEE division (~10 instructions,
+      // 48 per point) need not be taken: q = RN(t * RN(1/g)) differs from RN(t / g) by at most 3 * 2^-24 relative, so
+      // floor(q) is the exact index unless q lies within that distance of an integer; only then (tolerance 2^-21 * q:
+      // a few lanes in a thousand at the finest level) is the division evaluated.  Checked against the exact form on
+      // random and on knife-edge points by tests/test_hostemu.py (same source, host build).
+      const float q = t * G.rg[level][a];
+      fi = floorf(q);
+      const float fr = q - fi, tol = q * 4.76837158203125e-7f;
+      if (fr < tol || fr > 1.0f - tol) fi = floorf(pn_div(t, g));
+    }
     const int i = (int)fi;                                   // .int() : fi is integral, >= 0
     if (EXACT_W) {
       const float vmin = pn_add(pn_mul((float)i, g), G.bmin[a]);

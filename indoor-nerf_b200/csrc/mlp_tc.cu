@@ -314,21 +314,28 @@ __device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, 
   return mask;
 }
 
-#define PN_ROUND_SYNC() do { fence_async_smem(); fence_before_sync(); __syncthreads(); } while (0)
+// barrier over the 256 threads that run the MLP rounds: the whole CTA in the plain kernels, warps 0-7 in the
+// warp-specialised ones (whose scatter / gather warps never take part)
+__device__ __forceinline__ void mlp_sync() { named_bar_sync<1, 256>(); }
+#define PN_ROUND_SYNC() do { fence_async_smem(); fence_before_sync(); mlp_sync(); } while (0)
 
 // forward rounds shared by the forward kernel and the backward's recompute.
 // BWD = false: every 64-wide activation goes to A1.   BWD = true: H1 -> A1, colour hidden 1 -> A1C, 2 -> A2C.
 template <bool BWD>
 __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_t tmem, uint32_t lane_addr, uint64_t *bar,
                                            uint32_t &ph, int p, int half, const float *qrow, float &sigma,
-                                           float nraw[3], uint32_t &h1_mask) {
+                                           float nraw[3], uint32_t &h1_mask, uint64_t *r1_gate = nullptr,
+                                           uint32_t r1_gate_parity = 0, int a0_off = TS::A0, int cin_off = TS::CIN,
+                                           uint64_t *r3_release = nullptr) {
   const bool t0 = threadIdx.x == 0;
   uint8_t *a1c = BWD ? sm + TS::A1C : sm + TS::A1;
   uint8_t *a2c = BWD ? sm + TS::A2C : sm + TS::A1;
+  uint8_t *a0 = sm + a0_off, *cin = sm + cin_off;      // double-buffered by the warp-specialised forward
   // R1: H1 = relu(X S0^T)
   if (t0) {
+    if (r1_gate) mbar_wait(r1_gate, r1_gate_parity);   // D1 still holds the previous tile's dX until it is taken
     fence_after_sync();
-    issue(tmem + TM_D1, k_major(sm + TS::A0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
+    issue(tmem + TM_D1, k_major(a0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
     mma_commit(bar);
   }
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
@@ -347,17 +354,18 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     tmem_ld_wait();
     sigma = v[0];
     v[16] = 0.f;
-    st_chunk(sm + TS::CIN, chunk_off(p, 2, 4), v + 1);      // geo 0..7
-    st_chunk(sm + TS::CIN, chunk_off(p, 3, 4), v + 9);      // geo 8..14, 0
+    st_chunk(cin, chunk_off(p, 2, 4), v + 1);      // geo 0..7
+    st_chunk(cin, chunk_off(p, 3, 4), v + 9);      // geo 8..14, 0
   }
   PN_ROUND_SYNC();
   // R3: A1c = relu(CIN C0^T);  NH = relu(geo N0^T + b)
   if (t0) {
     fence_after_sync();
-    issue(tmem + TM_D1, k_major(sm + TS::CIN, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
+    issue(tmem + TM_D1, k_major(cin, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
     if (A.normals)
-      issue(tmem + TM_DN, k_major(sm + TS::CIN, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false);
+      issue(tmem + TM_DN, k_major(cin, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false);
     mma_commit(bar);
+    if (r3_release) mma_commit(r3_release);            // last reader of this tile's A0 / CIN buffer
   }
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
   epi_hidden32(lane_addr + TM_D1, a1c, p, half, nullptr);
@@ -454,6 +462,190 @@ mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__
   if (warp == 0) tmem_dealloc(tmem, TM_FWD_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Warp-specialised fused forward (pn_field_fwd_bf16): 8 MLP warps + GW gather warps per CTA, 2 CTAs per SM.
+//   gather warps (producers): evaluate the hash grid (and SH, keep mask, saved feature tile) of tile n+1 straight into
+//     the second A0 / CIN operand buffer while
+//   MLP warps (consumers) run the five MMA -> epilogue rounds of tile n.
+// full[b]  : 32*GW gather threads arrive after fence.proxy.async   -> gates the tile's first MMA (thread 0)
+// empty[b] : tcgen05.commit after the R3 MMAs (last readers of A0[b] / CIN[b]) -> gates the gather of tile n+2
+// In the single-role kernel the gather (L2 latency) and the round chain (MMA latency) of a tile are serial inside a
+// CTA: 2.7 ms per 12.6 M points against 1.7 ms (gather alone) and 1.6 ms (MLP alone).
+// ------------------------------------------------------------------------------------------------------
+struct FW {
+  static constexpr int A0B = TS::FWD_END;               // second [128 x 32] feature buffer
+  static constexpr int CINB = A0B + 128 * 32 * 2;       // second [128 x 32] colour-input buffer
+  static constexpr int END = CINB + 128 * 32 * 2;
+};
+
+template <int GW>
+__global__ void __launch_bounds__(kTcThreads + 32 * GW, 2)
+field_fwd_ws_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__restrict__ out) {
+  static_assert(GW == 4 || GW == 8, "4 gather warps (16 levels per thread) or 8 (8 levels per thread)");
+  constexpr int LPT = 16 / (GW / 4);                    // levels per gather thread
+  constexpr int kAuxRegs = GW == 4 ? 64 : 48, kMlpRegs = GW == 4 ? 88 : 80;
+  static_assert(256 * kMlpRegs + 32 * GW * kAuxRegs <= 65536 / 2, "register file at 2 CTAs/SM");
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar, full[2], empty[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  load_all_weights(sm, A);
+  if (warp == 0) tmem_alloc(&tmem_slot, TM_FWD_COLS);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&full[0], 32 * GW); mbar_init(&full[1], 32 * GW);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    mbar_fence_init();
+  }
+  fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
+
+  if (warp >= 8) {
+    // ---------------- gather role ----------------
+    setmaxnreg_dec<kAuxRegs>();
+    const int gw = warp - 8, gp = (gw & 3) * 32 + lane, lh = gw >> 2;
+    const int l_first = lh * LPT;
+    const bool quant = F.qparams != nullptr;
+    uint32_t n = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const int buf = n & 1;
+      uint8_t *a0 = sm + (buf ? FW::A0B : TS::A0), *cin = sm + (buf ? FW::CINB : TS::CIN);
+      const int64_t pt = tile * kTcTile + gp;
+      const bool valid = pt < A.in.n_points;
+      float xv[3] = {0.f, 0.f, 0.f};
+      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
+      // PIPE (4 gather warps, 64 registers): software pipeline over the levels — the 8 gathers of level l+1 are in
+      // flight while level l is interpolated.  With 8 gather warps (48 registers) the other warps cover the latency.
+      constexpr bool PIPE = GW == 4;
+      Cell c;
+      float2 e[8];
+      if (PIPE) {
+        point_cell<false>(F.G, l_first, xv, c);
+        const float2 *__restrict__ tab = F.T.t[l_first];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = __ldg(tab + corner_index(F.G, c, k));
+      }
+      if (n >= 2) mbar_wait(&empty[buf], ((n >> 1) - 1) & 1);    // tile n-2's MMAs have read this buffer
+      uint32_t word[4];
+#pragma unroll 4
+      for (int i = 0; i < LPT; ++i) {
+        const int l = l_first + i;
+        Cell cn;
+        float2 en[8];
+        if (PIPE) {
+          if (i + 1 < LPT) {
+            point_cell<false>(F.G, l + 1, xv, cn);
+            const float2 *__restrict__ tab = F.T.t[l + 1];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) en[k] = __ldg(tab + corner_index(F.G, cn, k));
+          }
+        } else {
+          point_cell<false>(F.G, l, xv, c);
+          const float2 *__restrict__ tab = F.T.t[l];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) e[k] = __ldg(tab + corner_index(F.G, c, k));
+        }
+        float e0[8], e1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { e0[k] = e[k].x; e1[k] = e[k].y; }
+        if (quant) {
+          const float *q = F.qparams + l * PN_QROW;
+          if (q[5] != 0.f) {
+            const float scale = q[0], rdenom = 1.0f / q[1], zp = q[2], qmin = q[3], qmax = q[4];
+            const bool train_form = q[6] != 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              e0[k] = fake_quant_fast(e0[k], scale, rdenom, zp, qmin, qmax, train_form);
+              e1[k] = fake_quant_fast(e1[k], scale, rdenom, zp, qmin, qmax, train_form);
+            }
+          }
+        }
+        const float f0 = valid ? trilerp_fast(e0, c.w) : 0.f, f1 = valid ? trilerp_fast(e1, c.w) : 0.f;
+        word[i & 3] = pack_bf16(f0, f1);
+        if ((i & 3) == 3) {                                       // 4 levels = one 16-byte chunk of the operand row
+          const uint32_t off = chunk_off(gp, l >> 2, 4);
+          const uint4 u = make_uint4(word[0], word[1], word[2], word[3]);
+          *reinterpret_cast<uint4 *>(a0 + off) = u;
+          if (F.featb) F.featb[tile * 512 + (off >> 4)] = u;      // the backward's operand tile, same layout
+        }
+        if (PIPE && i + 1 < LPT) {
+          c = cn;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) e[k] = en[k];
+        }
+      }
+      if (lh == 0) {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = 0.f;
+        if (valid) {
+          const int64_t r = pt / A.in.samples_per_ray;
+          sh4(__ldg(A.in.dirs + 3 * r), __ldg(A.in.dirs + 3 * r + 1), __ldg(A.in.dirs + 3 * r + 2), o);
+          if (F.keep_out) F.keep_out[pt] = point_keep(F.G, xv) ? 1 : 0;
+        }
+        st_chunk(cin, chunk_off(gp, 0, 4), o);
+        st_chunk(cin, chunk_off(gp, 1, 4), o + 8);
+      }
+      fence_async_smem();
+      mbar_arrive(&full[buf]);
+    }
+    __syncthreads();                                    // the CTA-wide barrier before the TMEM release below
+    return;
+  }
+
+  // ---------------- MLP role ----------------
+  setmaxnreg_inc<kMlpRegs>();
+  const int p = tid & 127, half = tid >> 7;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t ph = 0;
+  float q[8];
+  const float *qrow = nullptr;
+  if (A.in.act_q) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
+    if (q[5] != 0.f) qrow = q;
+  }
+  uint32_t n = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+    const int buf = n & 1;
+    const int64_t base = tile * kTcTile;
+    const bool valid = base + p < A.in.n_points;
+    float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
+    uint32_t m;
+    tc_forward<false>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, m, &full[buf], (n >> 1) & 1,
+                      buf ? FW::A0B : TS::A0, buf ? FW::CINB : TS::CIN, &empty[buf]);
+    // R5: rgb = A2c C2^T
+    if (tid == 0) {
+      fence_after_sync();
+      issue(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_C2, 64), instr_desc(128, 16, 0, 0), 4, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    if (half == 0) {
+      float v[16];
+      tmem_ld16(lane_addr + TM_D2, v);
+      tmem_ld_wait();
+      if (valid) {
+        const float xv[3] = {__ldg(F.pts + 3 * (base + p)), __ldg(F.pts + 3 * (base + p) + 1), __ldg(F.pts + 3 * (base + p) + 2)};
+        const bool kept = point_keep(F.G, xv);
+        float *o = out + (base + p) * A.C;
+        if (A.C == 4) {
+          *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], kept ? sigma : 0.f);
+        } else {
+          const float nn = fmaxf(sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]), 1e-12f);
+          o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = sigma;
+          o[4] = nraw[0] / nn; o[5] = nraw[1] / nn; o[6] = kept ? nraw[2] / nn : 0.f;
+        }
+      }
+    }
+    // no end-of-tile barrier: the next writer of D2 (R2 of the next tile) is issued behind the round barrier that
+    // follows R1's epilogue, which every thread reaches only after its reads above
+  }
+  fence_before_sync(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TM_FWD_COLS);
+}
+
 // masked in-place epilogue of an input-gradient GEMM, this thread's 32 columns:
 // tile row <- D * [tile row > 0] (or an explicit mask)
 __device__ __forceinline__ void epi_grad32(uint32_t taddr, uint8_t *tile, int p, int half, bool use_mask, uint32_t mask) {
@@ -499,22 +691,59 @@ __device__ __forceinline__ void flush_acc(uint32_t taddr, int ncols, bool owner,
   }
 }
 
-template <int SRC>
-__global__ void __launch_bounds__(kTcThreads, 2)
+// Warp-specialised variant (WS = true, fused scatter only): the CTA has 4 more warps (8..11) that do nothing but the
+// hash-grid scatter.  Warp 8+q owns TMEM lane quarter q = the 32 points of the tile whose feature gradients the last
+// MMA of the tile (B5) leaves in D1[0,32).  B5 commits to `dx_full` as well; the scatter warp copies its 32 x 32
+// block of dX out of TMEM into registers / local memory, arrives on `dx_empty` (which gates the next tile's first
+// MMA, the next writer of D1) and then walks the 16 levels while warps 0-7 are already in the ten MMA -> epilogue
+// rounds of the next tile.  The MLP rounds are a latency chain (~1.3 k cycles per round, one tile per CTA in flight);
+// the scatter is pure issue work (~60 % of the kernel's instructions) — run side by side they fill each other's
+// stalls instead of alternating.
+constexpr int kWsThreads = kTcThreads + 128;
+constexpr int kWsMlpRegs = 96, kWsAuxRegs = 48;     // (256 * 96 + 128 * 48) = 384 * 80: the CTA's allocation at 2 CTAs/SM
+
+template <int SRC, bool WS>
+__global__ void __launch_bounds__(WS ? kWsThreads : kTcThreads, 2)
 mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout,
                   float *__restrict__ dfeat, int64_t dfeat_stride, float *__restrict__ dsh, int64_t dsh_stride,
                   const pn_mlp_grads G) {
+  static_assert(!WS || SRC == SRC_TILE, "the warp-specialised backward is the fused field kernel");
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t bar;
-  const int tid = threadIdx.x, p = tid & 127, half = tid >> 7, warp = tid >> 5, lane = tid & 31;
+  __shared__ __align__(8) uint64_t bar, dx_full, dx_empty;
+  const int tid = threadIdx.x, p = tid & 127, half = (tid >> 7) & 1, warp = tid >> 5, lane = tid & 31;
   load_all_weights(sm, A);
   if (warp == 0) tmem_alloc(&tmem_slot, TM_BWD_COLS);
-  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&dx_full, 1); mbar_init(&dx_empty, 128); mbar_fence_init(); }
   fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  uint32_t ph = 0;
+  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
+  if (WS && warp >= 8) {
+    // ---------------- scatter role ----------------
+    setmaxnreg_dec<kWsAuxRegs>();
+    uint32_t phs = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t pt = tile * kTcTile + (warp - 8) * 32 + lane;
+      const bool valid = pt < A.in.n_points;
+      float xv[3] = {0.f, 0.f, 0.f};
+      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
+      float g[32];                                   // indexed by the rolled level loop -> local memory (L1-resident)
+      mbar_wait(&dx_full, phs); phs ^= 1; fence_after_sync();
+      tmem_ld16(lane_addr + TM_D1, g);
+      tmem_ld16(lane_addr + TM_D1 + 16, g + 16);
+      tmem_ld_wait();
+      fence_before_sync();
+      mbar_arrive(&dx_empty);
+#pragma unroll 1
+      for (int l = 0; l < F.G.n_levels; ++l)
+        scatter_level<false>(F.G, F.D.t[l], l, xv, valid ? g[2 * l] : 0.f, valid ? g[2 * l + 1] : 0.f, lane);
+    }
+    __syncthreads();                                 // the CTA-wide barrier before the TMEM release below
+    return;
+  }
+  if (WS) setmaxnreg_inc<kWsMlpRegs>();
+  uint32_t ph = 0, n_done = 0;
   float q[8];
   const float *qrow = nullptr;
   if (A.in.act_q) {
@@ -526,7 +755,6 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   float g_n2 = 0.f, g_n0[4] = {0.f, 0.f, 0.f, 0.f};
   const bool t0 = tid == 0;
   bool first = true;
-  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kTcTile;
     const bool valid = base + p < A.in.n_points;
@@ -539,7 +767,9 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     PN_ROUND_SYNC();
     float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
     uint32_t h1_mask;
-    tc_forward<true>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, h1_mask);
+    // WS: tile n's first MMA overwrites D1, which holds tile n-1's dX until phase n-1 of dx_empty completes
+    tc_forward<true>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, h1_mask,
+                     (WS && n_done > 0) ? &dx_empty : nullptr, (n_done - 1) & 1);
 
     // B0: cotangent tiles (half 0 owns the row-level values)
     if (half == 0) {
@@ -578,7 +808,7 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       g_n2 += s;
     }
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    if (A.normals) __syncthreads();                // all NH reads above are done
+    if (A.normals) mlp_sync();                     // all NH reads above are done
     epi_grad32(lane_addr + TM_D1, sm + TS::A2C, p, half, false, 0);
     if (A.normals) {
       float v[16];
@@ -666,9 +896,12 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       issue(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
       issue(tmem + TM_D1, k_major(sm + TS::A1, 64), mn_major(sm + TS::W_S0, 32), instr_desc(128, 32, 0, 1), 4, false);
       mma_commit(&bar);
+      if (WS) mma_commit(&dx_full);                    // the scatter warps' go-ahead: dX is complete in D1[0,32)
     }
-    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    if (SRC == SRC_TILE) {
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();  // (WS: A0 / A1 may be overwritten by the next tile from here)
+    if (WS) {
+      // nothing: warps 8-11 scatter this tile while this role moves on
+    } else if (SRC == SRC_TILE) {
       // Fused scatter.  A warp's 32 lanes are 32 consecutive samples, so the run-aggregated scatter applies
       // unchanged.  Half 0 scatters levels [0, split), half 1 the rest; each level's two gradients are read from
       // TMEM inside the loop so that the loop stays rolled (16 inlined copies of the scatter code thrashed the
@@ -696,7 +929,8 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       }
     }
     first = false;
-    fence_before_sync(); __syncthreads();
+    ++n_done;
+    if (!WS) { fence_before_sync(); mlp_sync(); }
   }
   // flush the weight gradients (every MMA has completed: the last commit was waited on)
   fence_after_sync();
@@ -778,6 +1012,28 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
     attr_set[dev] = true;
   }
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
+  // fused field forward: warp-specialised kernel by default (PN_FIELD_FWD=v1 selects the single-role kernel,
+  // PN_FWD_GW=4|8 the number of gather warps)
+  static int ws_gw = -1;
+  if (ws_gw < 0) {
+    const char *e = getenv("PN_FIELD_FWD"), *g = getenv("PN_FWD_GW");
+    ws_gw = (e && (e[0] == 'v' || e[0] == '0')) ? 0 : ((g && atoi(g) == 4) ? 4 : 8);
+  }
+  if (fused && !packed && ws_gw) {
+    static bool ws_attr[64] = {false};
+    if (dev >= 0 && dev < 64 && !ws_attr[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(field_fwd_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW::END);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(field_fwd_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW::END);
+      PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(field_fwd_ws): %s", cudaGetErrorString(e));
+      ws_attr[dev] = true;
+    }
+    const int64_t cap2 = (int64_t)sm_count() * 2;
+    const int blocks2 = (int)(tiles < cap2 ? tiles : cap2);
+    if (ws_gw == 4) field_fwd_ws_kernel<4><<<blocks2, kTcThreads + 128, FW::END, st>>>(A, F, out);
+    else field_fwd_ws_kernel<8><<<blocks2, kTcThreads + 256, FW::END, st>>>(A, F, out);
+    count_launch();
+    return check_launch("field_fwd_ws_kernel");
+  }
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int blocks = (int)(tiles < cap ? tiles : cap);
   if (packed) mlp_tc_fwd_kernel<3, SRC_PACKED><<<blocks, kTcThreads, smem, st>>>(A, F, out);
@@ -789,6 +1045,16 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
   return check_launch("mlp_tc_fwd_kernel");
 }
 
+// Which fused backward runs: the warp-specialised kernel (default) or the single-role one (PN_FIELD_BWD=v1).
+static bool bwd_ws_enabled() {
+  static int ws = -1;
+  if (ws < 0) {
+    const char *e = getenv("PN_FIELD_BWD");
+    ws = (e && (e[0] == 'v' || e[0] == '0')) ? 0 : 1;
+  }
+  return ws != 0;
+}
+
 static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const float *dout, float *dfeat,
                          int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads &dw, cudaStream_t st) {
   const int smem = TS::BWD_END;
@@ -796,16 +1062,21 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_F32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
   const int64_t cap = (int64_t)sm_count() * 2;          // 2 CTAs/SM: 2 x 256 TMEM columns, 2 x 107 KB smem
   const int blocks = (int)(tiles < cap ? tiles : cap);
-  if (fused) mlp_tc_bwd_kernel<SRC_TILE><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
-  else mlp_tc_bwd_kernel<SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
+  if (fused && bwd_ws_enabled())
+    mlp_tc_bwd_kernel<SRC_TILE, true><<<blocks, kWsThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
+  else if (fused)
+    mlp_tc_bwd_kernel<SRC_TILE, false><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
+  else
+    mlp_tc_bwd_kernel<SRC_F32, false><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
   count_launch();
   return check_launch("mlp_tc_bwd_kernel");
 }

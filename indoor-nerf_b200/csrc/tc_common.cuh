@@ -128,11 +128,30 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_addr, uint32_t pa
       : "memory");
   return ok;
 }
+// Bounded spin: a protocol bug must surface as a launch failure (trap), never as a GPU that hangs until the
+// watchdog of whoever launched us fires.  try_wait suspends in hardware for up to its time limit per probe,
+// so 2^22 failed probes is at least tens of milliseconds — orders of magnitude beyond any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
+  uint32_t spins = 0;
   while (!mbar_try_wait(a, parity)) {
+    if (++spins == (1u << 22)) __trap();
   }
 }
+// one arrival of the executing thread (release semantics at CTA scope)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier over a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+template <int ID, int THREADS>
+__device__ __forceinline__ void named_bar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
+}
+// register re-allocation between the roles of a warp-specialised CTA (all 4 warps of a warpgroup execute it)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 }  // namespace tc
 }  // namespace pn

@@ -60,6 +60,31 @@ void emu_hash_bwd(const pn_hash_grid *grid, float *const *dtables, const float *
   }
 }
 
+// Voxel indices of the bf16 paths' point_cell<false> (reciprocal multiply + exact-division fallback) next to the
+// reference form point_cell<true>; returns the number of (point, level, axis) triples where they differ (must be 0)
+// and, in *n_fallback, how often the fallback division was taken.
+int64_t emu_cell_index_mismatches(const pn_hash_grid *grid, const float *x, int64_t P, int64_t *n_fallback) {
+  const HashGridDev G = make_grid_dev(*grid);
+  int64_t bad = 0, fb = 0;
+  for (int64_t p = 0; p < P; ++p) {
+    const float xv[3] = {x[3 * p], x[3 * p + 1], x[3 * p + 2]};
+    for (int l = 0; l < G.n_levels; ++l) {
+      Cell a, b;
+      point_cell<true>(G, l, xv, a);
+      point_cell<false>(G, l, xv, b);
+      bad += (a.hx0 != b.hx0) + (a.hy0 != b.hy0) + (a.hz0 != b.hz0);
+      for (int ax = 0; ax < 3; ++ax) {
+        const float xc = fminf(fmaxf(xv[ax], G.bmin[ax]), G.bmax[ax]);
+        const float q = (xc - G.bmin[ax]) * G.rg[l][ax];
+        const float fr = q - floorf(q), tol = q * 4.76837158203125e-7f;
+        fb += (fr < tol || fr > 1.0f - tol);
+      }
+    }
+  }
+  if (n_fallback) *n_fallback = fb;
+  return bad;
+}
+
 void emu_sh4(const float *dirs, int64_t n, float *out) {
   for (int64_t i = 0; i < n; ++i) sh4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], out + 16 * i);
 }

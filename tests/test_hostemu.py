@@ -156,3 +156,32 @@ def test_rays_points_z(emu, golden):
     out = np.zeros_like(pts)
     emu.emu_make_points(fptr(o), fptr(d), fptr(zf), ctypes.c_int64(N), zf.shape[1], fptr(out))
     assert (out == pts).all()
+
+
+@pytest.mark.parametrize("finest,box", [(512, ((-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))),
+                                        (1024, ((-1.21, -0.93, -2.05), (1.37, 1.11, 0.49))),
+                                        (512, ((-4.7, -3.1, -0.2), (5.9, 7.3, 3.3)))])
+def test_fast_cell_index_equals_exact(emu, finest, box):
+    """The bf16 paths take the voxel index from a reciprocal multiply with an exact-division fallback
+    (hash_core.cuh point_cell<false>): it must equal the reference's floor((x - min) / g) (utils.py:108-110)
+    everywhere — random points, points outside the box, and points ON voxel boundaries at every level, where
+    the quotient sits within an ulp of an integer."""
+    bmin, bmax = np.array(box[0], np.float32), np.array(box[1], np.float32)
+    g = make_grid(bmin, bmax, finest, 19)
+    rng = np.random.default_rng(7)
+    pts = [rng.uniform(bmin - 0.05, bmax + 0.05, size=(200000, 3)).astype(np.float32)]
+    res = [float(r) for r in O.level_resolutions(16, finest)]
+    for r in res:                                   # knife edges: x = min + i * g (fp32), one ulp below, one ulp above
+        gs = ((bmax - bmin) / np.float32(r)).astype(np.float32)
+        i = rng.integers(0, int(r) + 1, size=(4000, 3)).astype(np.float32)
+        edge = (i * gs + bmin).astype(np.float32)
+        pts += [edge, np.nextafter(edge, np.float32(-np.inf)), np.nextafter(edge, np.float32(np.inf))]
+        q = rng.integers(0, int(r) + 1, size=(4000, 3)).astype(np.float32)      # and via the quotient: x = min + q / (1/g)
+        pts.append((q / (np.float32(1.0) / gs) + bmin).astype(np.float32))
+    x = np.ascontiguousarray(np.concatenate(pts, 0))
+    nfb = ctypes.c_int64(0)
+    emu.emu_cell_index_mismatches.restype = ctypes.c_int64
+    bad = emu.emu_cell_index_mismatches(ctypes.byref(g), fptr(x), ctypes.c_int64(x.shape[0]), ctypes.byref(nfb))
+    assert bad == 0, "%d voxel indices differ between the fast and the exact form" % bad
+    frac = nfb.value / (x.shape[0] * 16 * 3)
+    assert 0 < frac < 0.25, "fallback rate %.4f (expected: rare on random points, common on the knife edges)" % frac
