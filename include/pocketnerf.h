@@ -176,6 +176,12 @@ int pn_field_bwd_bf16(const pn_hash_grid *grid, float *const *dtables, const pn_
  * hardware.  D is the raw [128 lanes][N] accumulator. */
 int pn_tc_selftest(const int32_t *cfg, const float *A, const float *B, float *D, pn_stream_t stream);
 
+/* Diagnostic: install (buf != NULL) or remove a device buffer of 2 * cap_per_thread int64 into which the fused
+ * backward kernel's CTA 0 writes clock64() marks at the boundaries of its MMA -> epilogue rounds (thread 0 = the MMA
+ * issuer in [0, cap), thread 160 in [cap, 2 cap)): scripts/timeline_rounds.py turns them into a per-round latency
+ * table.  Never set in production; the kernels test one pointer per mark. */
+int pn_debug_timeline(int64_t *buf, int64_t cap_per_thread);
+
 /* ---- volume rendering ---------------------------------------------------------------------------- */
 
 /* raw2outputs (run_nerf.py:347-411).  raw[N,S,C] C = 4 or 7, z[N,S], rays_d[N,3], noise[N,S] or NULL

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "pn_field_bwd_bf16": [ctypes.POINTER(HashGrid), _P, ctypes.POINTER(MlpWeights), _P, _P, _P, _I, _P, _P, _P, _L,
                           ctypes.POINTER(MlpWeights), _P],
     "pn_tc_selftest": [_P, _P, _P, _P, _P],
+    "pn_debug_timeline": [_P, _L],
     "pn_tv_loss_fwd": [_P, _I, _I, _P, _P, _P, _P],
     "pn_tv_loss_bwd": [_P, _P, _I, _I, _P, _P, _P, _P],
     "pn_radam_step": [_P, _P, _P, _P, _L] + [ctypes.c_float] * 5 + [_I, _P],

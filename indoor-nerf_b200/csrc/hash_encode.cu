@@ -318,7 +318,9 @@ extern "C" int pn_hash_encode_bwd(const pn_hash_grid *grid, float *const *dtable
   const HashGridDev G = make_grid_dev(*grid);
   GradPtrs D;
   for (int l = 0; l < PN_MAX_LEVELS; ++l) D.t[l] = reinterpret_cast<float2 *>(dtables[l < grid->n_levels ? l : 0]);
-  for (int l = 0; l < grid->n_levels; ++l) PN_REQUIRE(dtables[l] != nullptr, PN_EINVAL, "dtables[%d] is NULL", l);
+  for (int l = 0; l < grid->n_levels; ++l)
+    PN_REQUIRE(dtables[l] != nullptr && ((uintptr_t)dtables[l] & 15) == 0, PN_EINVAL,
+               "dtables[%d] is NULL or not 16-byte aligned (paired 16-byte reductions)", l);
   const int blocks = hash_blocks(n_points, kHashThreads, 16);
   hash_bwd_kernel<<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, D, x, dfeat, n_points);
   count_launch();

@@ -134,8 +134,24 @@ struct FieldArgs {
   uint8_t *keep_out;    // forward: [P]
   uint4 *featb;         // bf16 feature tiles, 8 KB per 128-point tile, tile layout (forward writes, backward reads)
   int scatter_split;    // backward: half 0 scatters levels [0, split), half 1 the rest
+  int debug;            // PN_DEBUG_FLAGS (measurement only): 1 = skip the scatter work, 2 = skip the gather work
+  long long *tlog;      // pn_debug_timeline buffer: [2 threads][tlog_cap] clock64 marks, or NULL
+  int tlog_cap;
   PackedDev PK;         // SRC_PACKED: tables as integer codes (inference)
 };
+
+// Diagnostic timeline (pn_debug_timeline): when a log buffer is installed, two threads of CTA 0 — thread 0 (the MMA
+// issuer) and thread 160 (an ordinary epilogue thread) — write clock64() at the marked points of every round of their
+// first tiles.  One predictable branch per mark otherwise; never set in production runs.
+struct TLog {
+  long long *p;
+  int i, cap;
+  __device__ __forceinline__ void mark() {
+    if (p && i < cap) p[i++] = clock64();
+  }
+};
+static long long *g_tlog_buf = nullptr;
+static int g_tlog_cap = 0;
 
 // input source of a tile's hash features
 enum { SRC_F32 = 0, SRC_HASH = 1, SRC_TILE = 2, SRC_PACKED = 3 };
@@ -231,7 +247,7 @@ __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, con
     for (int i = 0; i < 8; ++i) {
       const int l = half * 8 + i;
       float f0 = 0.f, f1 = 0.f;
-      if (l < F->G.n_levels && valid) {
+      if (l < F->G.n_levels && valid && !(F->debug & 2)) {
         Cell c;
         point_cell<false>(F->G, l, xv, c);
         float e0[8], e1[8];
@@ -326,28 +342,37 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
                                            uint32_t &ph, int p, int half, const float *qrow, float &sigma,
                                            float nraw[3], uint32_t &h1_mask, uint64_t *r1_gate = nullptr,
                                            uint32_t r1_gate_parity = 0, int a0_off = TS::A0, int cin_off = TS::CIN,
-                                           uint64_t *r3_release = nullptr) {
+                                           uint64_t *r3_release = nullptr, TLog *tl = nullptr) {
+  TLog none = {nullptr, 0, 0};
+  TLog &T = tl ? *tl : none;
   const bool t0 = threadIdx.x == 0;
   uint8_t *a1c = BWD ? sm + TS::A1C : sm + TS::A1;
   uint8_t *a2c = BWD ? sm + TS::A2C : sm + TS::A1;
   uint8_t *a0 = sm + a0_off, *cin = sm + cin_off;      // double-buffered by the warp-specialised forward
   // R1: H1 = relu(X S0^T)
+  T.mark();
   if (t0) {
     if (r1_gate) mbar_wait(r1_gate, r1_gate_parity);   // D1 still holds the previous tile's dX until it is taken
     fence_after_sync();
     issue(tmem + TM_D1, k_major(a0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
     mma_commit(bar);
   }
+  T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
+  T.mark();
   h1_mask = epi_hidden32(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
+  T.mark();
   PN_ROUND_SYNC();
   // R2: [sigma, geo] = H1 S1^T
+  T.mark();
   if (t0) {
     fence_after_sync();
     issue(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false);
     mma_commit(bar);
   }
+  T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
+  T.mark();
   if (half == 0) {
     float v[17];
     tmem_ld16(lane_addr + TM_D2, v);
@@ -357,8 +382,10 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     st_chunk(cin, chunk_off(p, 2, 4), v + 1);      // geo 0..7
     st_chunk(cin, chunk_off(p, 3, 4), v + 9);      // geo 8..14, 0
   }
+  T.mark();
   PN_ROUND_SYNC();
   // R3: A1c = relu(CIN C0^T);  NH = relu(geo N0^T + b)
+  T.mark();
   if (t0) {
     fence_after_sync();
     issue(tmem + TM_D1, k_major(cin, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
@@ -367,7 +394,9 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     mma_commit(bar);
     if (r3_release) mma_commit(r3_release);            // last reader of this tile's A0 / CIN buffer
   }
+  T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
+  T.mark();
   epi_hidden32(lane_addr + TM_D1, a1c, p, half, nullptr);
   if (A.normals) {
     const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + half * 16;
@@ -379,8 +408,10 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     st_chunk(sm + TS::NH, chunk_off(p, half * 2, 4), v);
     st_chunk(sm + TS::NH, chunk_off(p, half * 2 + 1, 4), v + 8);
   }
+  T.mark();
   PN_ROUND_SYNC();
   // R4: A2c = relu(A1c C1^T);  raw normal = NH N2^T + b
+  T.mark();
   if (t0) {
     fence_after_sync();
     issue(tmem + TM_D1, k_major(a1c, 64), k_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 0), 4, false);
@@ -388,7 +419,9 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
       issue(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false);
     mma_commit(bar);
   }
+  T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
+  T.mark();
   if (A.normals && half == 0) {
     const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + 32;
     float v[16];
@@ -397,6 +430,7 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
     nraw[0] = v[0] + bias[0]; nraw[1] = v[1] + bias[1]; nraw[2] = v[2] + bias[2];
   }
   epi_hidden32(lane_addr + TM_D1, a2c, p, half, nullptr);
+  T.mark();
   PN_ROUND_SYNC();
 }
 
@@ -520,6 +554,18 @@ field_fwd_ws_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *
       constexpr bool PIPE = GW == 4;
       Cell c;
       float2 e[8];
+      if (F.debug & 2) {
+        if (n >= 2) mbar_wait(&empty[buf], ((n >> 1) - 1) & 1);
+        for (int i = 0; i < LPT; i += 4)
+          *reinterpret_cast<uint4 *>(a0 + chunk_off(gp, (l_first + i) >> 2, 4)) = make_uint4(0u, 0u, 0u, 0u);
+        if (lh == 0) {
+          *reinterpret_cast<uint4 *>(cin + chunk_off(gp, 0, 4)) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4 *>(cin + chunk_off(gp, 1, 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_async_smem();
+        mbar_arrive(&full[buf]);
+        continue;
+      }
       if (PIPE) {
         point_cell<false>(F.G, l_first, xv, c);
         const float2 *__restrict__ tab = F.T.t[l_first];
@@ -735,6 +781,7 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       tmem_ld_wait();
       fence_before_sync();
       mbar_arrive(&dx_empty);
+      if (F.debug & 1) continue;
 #pragma unroll 1
       for (int l = 0; l < F.G.n_levels; ++l)
         scatter_level<false>(F.G, F.D.t[l], l, xv, valid ? g[2 * l] : 0.f, valid ? g[2 * l + 1] : 0.f, lane);
@@ -744,6 +791,8 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   }
   if (WS) setmaxnreg_inc<kWsMlpRegs>();
   uint32_t ph = 0, n_done = 0;
+  TLog T = {nullptr, 0, F.tlog_cap};
+  if (F.tlog && blockIdx.x == 0 && (tid == 0 || tid == 160)) T.p = F.tlog + (tid ? F.tlog_cap : 0);
   float q[8];
   const float *qrow = nullptr;
   if (A.in.act_q) {
@@ -758,18 +807,20 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kTcTile;
     const bool valid = base + p < A.in.n_points;
+    T.mark();
     tc_load_inputs<SRC>(sm, A, &F, tile, base, p, half, valid);
     float d_o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (valid) {
       for (int c = 0; c < A.C; ++c) d_o[c] = __ldg(dout + (base + p) * A.C + c);
       if (A.in.keep && A.in.keep[base + p] == 0) d_o[A.C - 1] = 0.f;            // run_nerf.py:66
     }
+    T.mark();
     PN_ROUND_SYNC();
     float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
     uint32_t h1_mask;
     // WS: tile n's first MMA overwrites D1, which holds tile n-1's dX until phase n-1 of dx_empty completes
     tc_forward<true>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, h1_mask,
-                     (WS && n_done > 0) ? &dx_empty : nullptr, (n_done - 1) & 1);
+                     (WS && n_done > 0) ? &dx_empty : nullptr, (n_done - 1) & 1, TS::A0, TS::CIN, nullptr, &T);
 
     // B0: cotangent tiles (half 0 owns the row-level values)
     if (half == 0) {
@@ -790,8 +841,10 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
         st_chunk(sm + TS::DNR, chunk_off(p, 1, 2), z);
       }
     }
+    T.mark();
     PN_ROUND_SYNC();
     // B1: dC2^T += A2c^T dOut ; dA2 = dOut C2 ; (normals) dNH = dNraw N2
+    T.mark();
     if (t0) {
       fence_after_sync();
       issue(tmem + TM_GC2, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::DOUT, 16), instr_desc(64, 16, 1, 1), 8, !first);
@@ -807,7 +860,9 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
         s += tile_elem(sm + TS::DNR, r, j, 2) * (tid < 96 ? tile_elem(sm + TS::NH, r, k, 4) : 1.f);
       g_n2 += s;
     }
+    T.mark();
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    T.mark();
     if (A.normals) mlp_sync();                     // all NH reads above are done
     epi_grad32(lane_addr + TM_D1, sm + TS::A2C, p, half, false, 0);
     if (A.normals) {
@@ -823,8 +878,10 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
         st_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), v + 8 * c);
       }
     }
+    T.mark();
     PN_ROUND_SYNC();
     // B2: dC1 += dA2pre^T A1c ; dA1 = dA2pre C1
+    T.mark();
     if (t0) {
       fence_after_sync();
       issue(tmem + TM_GC1, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::A1C, 64), instr_desc(64, 64, 1, 1), 8, !first);
@@ -840,10 +897,14 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
           g_n0[i] += d * ((k0 + i) < 15 ? tile_elem(sm + TS::CIN, r, 16 + k0 + i, 4) : 1.f);
       }
     }
+    T.mark();
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    T.mark();
     epi_grad32(lane_addr + TM_D1, sm + TS::A1C, p, half, false, 0);
+    T.mark();
     PN_ROUND_SYNC();
     // B3: dC0 += dA1pre^T CIN ; dCIN = dA1pre C0 ; (normals) dgeo_n = dNHpre N0
+    T.mark();
     if (t0) {
       fence_after_sync();
       issue(tmem + TM_GC0, mn_major(sm + TS::A1C, 64), mn_major(sm + TS::CIN, 32), instr_desc(64, 32, 1, 1), 8, !first);
@@ -852,7 +913,9 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
         issue(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false);
       mma_commit(&bar);
     }
+    T.mark();
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    T.mark();
     if (half == 0) {
       if (dsh) {                                       // dCIN[0..16) = d SH
         float v[16];
@@ -879,18 +942,24 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       st_chunk(sm + TS::DH2, chunk_off(p, 0, 2), g);
       st_chunk(sm + TS::DH2, chunk_off(p, 1, 2), g + 8);
     }
+    T.mark();
     PN_ROUND_SYNC();
     // B4: dS1^T += H1^T dH2 ; dH1 = dH2 S1
+    T.mark();
     if (t0) {
       fence_after_sync();
       issue(tmem + TM_GS1, mn_major(sm + TS::A1, 64), mn_major(sm + TS::DH2, 16), instr_desc(64, 16, 1, 1), 8, !first);
       issue(tmem + TM_D1, k_major(sm + TS::DH2, 16), mn_major(sm + TS::W_S1, 64), instr_desc(128, 64, 0, 1), 1, false);
       mma_commit(&bar);
     }
+    T.mark();
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    T.mark();
     epi_grad32(lane_addr + TM_D1, sm + TS::A1, p, half, true, h1_mask);
+    T.mark();
     PN_ROUND_SYNC();
     // B5: dS0 += dH1pre^T X ; dX = dH1pre S0
+    T.mark();
     if (t0) {
       fence_after_sync();
       issue(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
@@ -898,7 +967,9 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       mma_commit(&bar);
       if (WS) mma_commit(&dx_full);                    // the scatter warps' go-ahead: dX is complete in D1[0,32)
     }
-    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();  // (WS: A0 / A1 may be overwritten by the next tile from here)
+    T.mark();
+    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
+    T.mark();  // (WS: A0 / A1 may be overwritten by the next tile from here)
     if (WS) {
       // nothing: warps 8-11 scatter this tile while this role moves on
     } else if (SRC == SRC_TILE) {
@@ -910,7 +981,8 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       const int kSplit = F.scatter_split;
       float xv[3] = {0.f, 0.f, 0.f};
       if (valid) { xv[0] = __ldg(F.pts + 3 * (base + p)); xv[1] = __ldg(F.pts + 3 * (base + p) + 1); xv[2] = __ldg(F.pts + 3 * (base + p) + 2); }
-      const int l0 = half ? kSplit : 0, l1 = half ? F.G.n_levels : (kSplit < F.G.n_levels ? kSplit : F.G.n_levels);
+      const int l0 = half ? kSplit : 0,
+                l1 = (F.debug & 1) ? 0 : (half ? F.G.n_levels : (kSplit < F.G.n_levels ? kSplit : F.G.n_levels));
 #pragma unroll 2
       for (int l = l0; l < l1; ++l) {
         float g0, g1;
@@ -928,6 +1000,7 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
         for (int c = 0; c < 4; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
     }
+    T.mark();
     first = false;
     ++n_done;
     if (!WS) { fence_before_sync(); mlp_sync(); }
@@ -959,9 +1032,359 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   if (warp == 0) tmem_dealloc(tmem, TM_BWD_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Fused backward, third structure (pn_field_bwd_bf16, PN_FIELD_BWD=v3): three roles per CTA, 2 CTAs per SM.
+//   warps 0-7   epilogue: TMEM -> ReLU mask / bf16 -> operand tiles (thread = row x column half), as before
+//   warps 8-11  scatter : take the tile's dX out of TMEM and walk the 16 hash levels (as in the WS kernel)
+//   warp  12    MMA     : waits for `ready` (8 arrivals: one elected lane per epilogue warp), issues the round's
+//                         tcgen05.mma from warp-uniform control flow with precomputed descriptor words, commits to
+//                         `done`; between rounds it prefetches the next tile's inputs into L2.
+// What the clock64 timeline of the single-role kernel showed per 128-point tile (33 k cycles): 3.0 k waiting for the
+// saved feature tile and 2.4 k for the cotangent rows (DRAM latency, exposed once each), 6 k in thread 0 building
+// descriptors and issuing the 78 MMAs of a tile (~80 cycles each from a divergent branch), 16 k in the scatter; the MMAs
+// themselves and the epilogues are ~1 k and ~2 k.  Here the epilogue warps never issue or meet at a CTA barrier: they
+// arrive on `ready` and go straight to waiting on `done`.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kV3Threads = kTcThreads + 128 + 32;
+constexpr int kV3EpiRegs = 80, kV3AuxRegs = 56;          // 256*80 + 128*56 + 32*72 = 416*72 (launch bound at 2 CTAs/SM)
+
+struct DescW {
+  uint32_t lo, hi, adv;                                   // descriptor words; adv = start-address step per K=16, in 16 B units
+};
+__device__ __forceinline__ DescW desc_words(const Opnd &o) {
+  DescW d;
+  d.lo = ((o.addr & 0x3FFFFu) >> 4) | (((o.lbo >> 4) & 0x3FFFu) << 16);
+  d.hi = ((o.sbo >> 4) & 0x3FFFu) | (1u << 14);
+  d.adv = o.adv >> 4;
+  return d;
+}
+__device__ __forceinline__ void issue3(uint32_t d, const Opnd &a, const Opnd &b, uint32_t idesc, int ksteps, bool accumulate) {
+  const DescW da = desc_words(a), db = desc_words(b);
+#pragma unroll
+  for (int k = 0; k < ksteps; ++k)
+    mma_f16(d, ((uint64_t)da.hi << 32) | (uint64_t)(da.lo + k * da.adv), ((uint64_t)db.hi << 32) | (uint64_t)(db.lo + k * db.adv),
+            idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+
+// epilogue warps: this round's operand tiles are written -> one arrival per warp on `ready`
+__device__ __forceinline__ void epi_arrive(uint64_t *ready, int lane) {
+  fence_async_smem();
+  fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(ready);
+}
+__device__ __forceinline__ void epi_wait(uint64_t *done, uint32_t &ph) {
+  mbar_wait(done, ph);
+  ph ^= 1;
+  fence_after_sync();
+}
+
+__global__ void __launch_bounds__(kV3Threads, 2)
+field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout, const pn_mlp_grads G) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t ready, done, dx_full, dx_empty;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = uniform_warp_idx();
+  load_all_weights(sm, A);
+  if (warp == 0) tmem_alloc(&tmem_slot, TM_BWD_COLS);
+  if (tid == 0) {
+    mbar_init(&ready, 8); mbar_init(&done, 1); mbar_init(&dx_full, 1); mbar_init(&dx_empty, 128);
+    mbar_fence_init();
+  }
+  fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
+  const int C = A.C;
+
+  if (warp == 12) {
+    // ---------------- MMA role ----------------
+    const bool lead = elect_one();
+    uint32_t pr = 0, n = 0;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      // next tile's inputs -> L2 (saved feature tile 8 KB, cotangent rows, positions, keep flags)
+      const int64_t nt = tile + gridDim.x;
+      if (lead && nt < n_tiles) {
+        const int64_t nb = nt * kTcTile;
+        const int64_t rows = (A.in.n_points - nb) < kTcTile ? (A.in.n_points - nb) : kTcTile;
+        prefetch_l2(F.featb + nt * 512, 8192);
+        const uint32_t db = (uint32_t)(rows * C * 4) & ~15u, pb = (uint32_t)(rows * 12) & ~15u;
+        if (db && (((uintptr_t)(dout + nb * C)) & 15) == 0) prefetch_l2(dout + nb * C, db);
+        if (pb && (((uintptr_t)(F.pts + nb * 3)) & 15) == 0) prefetch_l2(F.pts + nb * 3, pb);
+      }
+#define PN_MMA_ROUND(...)                                         \
+  do {                                                            \
+    mbar_wait(&ready, pr); pr ^= 1; fence_after_sync();           \
+    if (lead) { __VA_ARGS__; mma_commit(&done); }                 \
+    __syncwarp();                                                 \
+  } while (0)
+      // R1 (D1 still holds the previous tile's dX until the scatter warps have taken it)
+      mbar_wait(&ready, pr); pr ^= 1;
+      if (n > 0) mbar_wait(&dx_empty, (n - 1) & 1);
+      fence_after_sync();
+      if (lead) {
+        issue3(tmem + TM_D1, k_major(sm + TS::A0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
+        mma_commit(&done);
+      }
+      __syncwarp();
+      PN_MMA_ROUND(issue3(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false));
+      PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::CIN, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
+                   if (A.normals) issue3(tmem + TM_DN, k_major(sm + TS::CIN, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false));
+      PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), k_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 0), 4, false);
+                   if (A.normals) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false));
+      // B1: dC2^T += A2c^T dOut ; dA2 = dOut C2 ; (normals) dNH = dNraw N2
+      PN_MMA_ROUND(issue3(tmem + TM_GC2, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::DOUT, 16), instr_desc(64, 16, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::DOUT, 16), mn_major(sm + TS::W_C2, 64), instr_desc(128, 64, 0, 1), 1, false);
+                   if (A.normals) issue3(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false));
+      // B2: dC1 += dA2pre^T A1c ; dA1 = dA2pre C1
+      PN_MMA_ROUND(issue3(tmem + TM_GC1, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::A1C, 64), instr_desc(64, 64, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::A2C, 64), mn_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 1), 4, false));
+      // B3: dC0 += dA1pre^T CIN ; dCIN = dA1pre C0 ; (normals) dgeo_n = dNHpre N0
+      PN_MMA_ROUND(issue3(tmem + TM_GC0, mn_major(sm + TS::A1C, 64), mn_major(sm + TS::CIN, 32), instr_desc(64, 32, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), mn_major(sm + TS::W_C0, 32), instr_desc(128, 32, 0, 1), 4, false);
+                   if (A.normals) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false));
+      // B4: dS1^T += H1^T dH2 ; dH1 = dH2 S1
+      PN_MMA_ROUND(issue3(tmem + TM_GS1, mn_major(sm + TS::A1, 64), mn_major(sm + TS::DH2, 16), instr_desc(64, 16, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::DH2, 16), mn_major(sm + TS::W_S1, 64), instr_desc(128, 64, 0, 1), 1, false));
+      // B5: dS0 += dH1pre^T X ; dX = dH1pre S0 -> also the scatter warps' go-ahead
+      PN_MMA_ROUND(issue3(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::A1, 64), mn_major(sm + TS::W_S0, 32), instr_desc(128, 32, 0, 1), 4, false);
+                   mma_commit(&dx_full));
+#undef PN_MMA_ROUND
+      first = false;
+    }
+    __syncthreads();
+    return;
+  }
+
+  if (warp >= 8) {
+    // ---------------- scatter role ----------------
+    setmaxnreg_dec<kV3AuxRegs>();
+    uint32_t phs = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t pt = tile * kTcTile + (warp - 8) * 32 + lane;
+      const bool valid = pt < A.in.n_points;
+      float xv[3] = {0.f, 0.f, 0.f};
+      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
+      float g[32];
+      mbar_wait(&dx_full, phs); phs ^= 1; fence_after_sync();
+      tmem_ld16(lane_addr + TM_D1, g);
+      tmem_ld16(lane_addr + TM_D1 + 16, g + 16);
+      tmem_ld_wait();
+      fence_before_sync();
+      mbar_arrive(&dx_empty);
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) any = any || (g[j] != 0.f);
+      if (!__any_sync(0xffffffffu, valid && any) || (F.debug & 1)) continue;     // 32 samples without a gradient (empty space)
+#pragma unroll 1
+      for (int l = 0; l < F.G.n_levels; ++l)
+        scatter_level<false>(F.G, F.D.t[l], l, xv, valid ? g[2 * l] : 0.f, valid ? g[2 * l + 1] : 0.f, lane);
+    }
+    __syncthreads();
+    return;
+  }
+
+  // ---------------- epilogue role ----------------
+  setmaxnreg_inc<kV3EpiRegs>();
+  const int p = tid & 127, half = tid >> 7;
+  uint32_t ph = 0;
+  float q[8];
+  const float *qrow = nullptr;
+  if (A.in.act_q) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
+    if (q[5] != 0.f) qrow = q;
+  }
+  float g_n2 = 0.f, g_n0[4] = {0.f, 0.f, 0.f, 0.f};
+  bool first = true;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kTcTile;
+    const bool valid = base + p < A.in.n_points;
+    // the previous tile's B5 (reader of A0 / A1) was waited for at the end of the previous iteration
+    tc_load_inputs<SRC_TILE>(sm, A, &F, tile, base, p, half, valid);
+    float d_o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      if (C == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(dout + (base + p) * 4));
+        d_o[0] = v.x; d_o[1] = v.y; d_o[2] = v.z; d_o[3] = v.w;
+        if (A.in.keep && A.in.keep[base + p] == 0) d_o[3] = 0.f;                  // run_nerf.py:66
+      } else {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) d_o[c] = __ldg(dout + (base + p) * 7 + c);
+        if (A.in.keep && A.in.keep[base + p] == 0) d_o[6] = 0.f;
+      }
+    }
+    epi_arrive(&ready, lane);
+    // E1: H1 = relu(D1) -> A1
+    epi_wait(&done, ph);
+    const uint32_t h1_mask = epi_hidden32(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
+    epi_arrive(&ready, lane);
+    // E2: [sigma, geo] -> CIN[16..32)
+    epi_wait(&done, ph);
+    if (half == 0) {
+      float v[17];
+      tmem_ld16(lane_addr + TM_D2, v);
+      tmem_ld_wait();
+      v[16] = 0.f;
+      st_chunk(sm + TS::CIN, chunk_off(p, 2, 4), v + 1);
+      st_chunk(sm + TS::CIN, chunk_off(p, 3, 4), v + 9);
+    }
+    epi_arrive(&ready, lane);
+    // E3: colour hidden 1 -> A1C ; (normals) NH
+    epi_wait(&done, ph);
+    epi_hidden32(lane_addr + TM_D1, sm + TS::A1C, p, half, nullptr);
+    if (A.normals) {
+      const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + half * 16;
+      float v[16];
+      tmem_ld16(lane_addr + TM_DN + half * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + bias[j], 0.f);
+      st_chunk(sm + TS::NH, chunk_off(p, half * 2, 4), v);
+      st_chunk(sm + TS::NH, chunk_off(p, half * 2 + 1, 4), v + 8);
+    }
+    epi_arrive(&ready, lane);
+    // E4: colour hidden 2 -> A2C ; raw normal ; B0: cotangent tiles
+    epi_wait(&done, ph);
+    float nraw[3] = {0.f, 0.f, 0.f};
+    if (A.normals && half == 0) {
+      const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + 32;
+      float v[16];
+      tmem_ld16(lane_addr + TM_D2, v);
+      tmem_ld_wait();
+      nraw[0] = v[0] + bias[0]; nraw[1] = v[1] + bias[1]; nraw[2] = v[2] + bias[2];
+    }
+    epi_hidden32(lane_addr + TM_D1, sm + TS::A2C, p, half, nullptr);
+    if (half == 0) {
+      float v[8] = {d_o[0], d_o[1], d_o[2], 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      st_chunk(sm + TS::DOUT, chunk_off(p, 0, 2), v);
+      st_chunk(sm + TS::DOUT, chunk_off(p, 1, 2), z);
+      if (A.normals) {
+        const float nn = sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]);
+        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (nn > 1e-12f) {
+          const float m0 = nraw[0] / nn, m1 = nraw[1] / nn, m2 = nraw[2] / nn;
+          const float dot = m0 * d_o[4] + m1 * d_o[5] + m2 * d_o[6];
+          r[0] = (d_o[4] - m0 * dot) / nn; r[1] = (d_o[5] - m1 * dot) / nn; r[2] = (d_o[6] - m2 * dot) / nn;
+        } else {
+          r[0] = d_o[4] / 1e-12f; r[1] = d_o[5] / 1e-12f; r[2] = d_o[6] / 1e-12f;
+        }
+        st_chunk(sm + TS::DNR, chunk_off(p, 0, 2), r);
+        st_chunk(sm + TS::DNR, chunk_off(p, 1, 2), z);
+      }
+    }
+    epi_arrive(&ready, lane);
+    // normal head weight gradients on the CUDA cores (611 numbers): every row of NH / DNR must be written first
+    if (A.normals) {
+      mlp_sync();
+      if (tid < 99) {
+        const int j = tid < 96 ? tid >> 5 : tid - 96, k = tid & 31;
+        float s = 0.f;
+        for (int r = 0; r < kTcTile; ++r)
+          s += tile_elem(sm + TS::DNR, r, j, 2) * (tid < 96 ? tile_elem(sm + TS::NH, r, k, 4) : 1.f);
+        g_n2 += s;
+      }
+    }
+    // E(B1): dA2pre -> A2C (in place, masked) ; (normals) dNHpre -> NH
+    epi_wait(&done, ph);
+    if (A.normals) mlp_sync();                     // all NH reads above are done
+    epi_grad32(lane_addr + TM_D1, sm + TS::A2C, p, half, false, 0);
+    if (A.normals) {
+      float v[16];
+      tmem_ld16(lane_addr + TM_DN + half * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float a[8];
+        ld_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * c + j] = a[j] > 0.f ? v[8 * c + j] : 0.f;
+        st_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), v + 8 * c);
+      }
+    }
+    epi_arrive(&ready, lane);
+    if (A.normals) {
+      mlp_sync();                                  // dNHpre rows of every thread are written
+      if (tid < 128) {                             // dN0w[j][k] (k < 15) and dN0b[j] (k == 15): 4 outputs per thread
+        const int j = tid >> 2, k0 = (tid & 3) * 4;
+        for (int r = 0; r < kTcTile; ++r) {
+          const float d = tile_elem(sm + TS::NH, r, j, 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            g_n0[i] += d * ((k0 + i) < 15 ? tile_elem(sm + TS::CIN, r, 16 + k0 + i, 4) : 1.f);
+        }
+      }
+    }
+    // E(B2): dA1pre -> A1C
+    epi_wait(&done, ph);
+    epi_grad32(lane_addr + TM_D1, sm + TS::A1C, p, half, false, 0);
+    epi_arrive(&ready, lane);
+    // E(B3): [dsigma, dgeo] -> DH2
+    epi_wait(&done, ph);
+    if (half == 1) {
+      float g[17];
+      tmem_ld16(lane_addr + TM_D1 + 16, g + 1);        // dCIN[16..32) = dgeo[0..15) + pad
+      tmem_ld_wait();
+      if (A.normals) {
+        float v[16];
+        tmem_ld16(lane_addr + TM_D2, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 15; ++j) g[1 + j] += v[j];
+      }
+      g[0] = d_o[3];                                   // dsigma (keep mask applied above when C == 4)
+      st_chunk(sm + TS::DH2, chunk_off(p, 0, 2), g);
+      st_chunk(sm + TS::DH2, chunk_off(p, 1, 2), g + 8);
+    }
+    epi_arrive(&ready, lane);
+    // E(B4): dH1pre -> A1
+    epi_wait(&done, ph);
+    epi_grad32(lane_addr + TM_D1, sm + TS::A1, p, half, true, h1_mask);
+    epi_arrive(&ready, lane);
+    // B5 reads A1 and A0: wait for it before the next tile's inputs overwrite them
+    epi_wait(&done, ph);
+    first = false;
+  }
+  // flush the weight gradients (every MMA has completed: the last commit was waited on)
+  if (!first && warp < 4) {
+    const bool owner = lane < 16;
+    const int row = warp * 16 + lane;
+    flush_acc(lane_addr + TM_GC1, 64, owner, row, G.c1, 64, 64, 64, false);
+    flush_acc(lane_addr + TM_GS0, 32, owner, row, G.s0, 32, 64, 32, false);
+    flush_acc(lane_addr + TM_GC0, 32, owner, row, G.c0, 31, 64, 31, false);
+    flush_acc(lane_addr + TM_GS1, 16, owner, row, G.s1, 64, 64, 16, true);
+    flush_acc(lane_addr + TM_GC2, 16, owner, row, G.c2, 64, 64, 3, true);
+  }
+  if (!first && A.normals) {
+    if (tid < 96) { if (G.n2w) atomicAdd(G.n2w + (tid >> 5) * 32 + (tid & 31), g_n2); }
+    else if (tid < 99) { if (G.n2b) atomicAdd(G.n2b + (tid - 96), g_n2); }
+    if (tid < 128) {
+      const int j = tid >> 2, k0 = (tid & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (k0 + i < 15) { if (G.n0w) atomicAdd(G.n0w + j * 15 + k0 + i, g_n0[i]); }
+        else if (G.n0b) atomicAdd(G.n0b + j, g_n0[i]);
+      }
+    }
+  }
+  fence_before_sync(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TM_BWD_COLS);
+}
+
 }  // namespace pn
 
 using namespace pn;
+
+extern "C" int pn_debug_timeline(int64_t *buf, int64_t cap_per_thread) {
+  PN_REQUIRE(cap_per_thread >= 0 && cap_per_thread < (1 << 20), PN_EINVAL, "cap_per_thread %lld", (long long)cap_per_thread);
+  pn::g_tlog_buf = reinterpret_cast<long long *>(buf);
+  pn::g_tlog_cap = buf ? (int)cap_per_thread : 0;
+  return 0;
+}
 
 extern "C" int pn_tc_selftest(const int32_t *cfg, const float *A, const float *B, float *D, pn_stream_t stream) {
   PN_REQUIRE(cfg && A && B && D, PN_EINVAL, "NULL pointer argument");
@@ -1012,12 +1435,11 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
     attr_set[dev] = true;
   }
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
-  // fused field forward: warp-specialised kernel by default (PN_FIELD_FWD=v1 selects the single-role kernel,
-  // PN_FWD_GW=4|8 the number of gather warps)
+  // fused field forward: PN_FIELD_FWD=ws selects the warp-specialised kernel (PN_FWD_GW=4|8 gather warps)
   static int ws_gw = -1;
   if (ws_gw < 0) {
     const char *e = getenv("PN_FIELD_FWD"), *g = getenv("PN_FWD_GW");
-    ws_gw = (e && (e[0] == 'v' || e[0] == '0')) ? 0 : ((g && atoi(g) == 4) ? 4 : 8);
+    ws_gw = (e && e[0] == 'w') ? ((g && atoi(g) == 4) ? 4 : 8) : 0;      // default: single-role kernel (measured faster)
   }
   if (fused && !packed && ws_gw) {
     static bool ws_attr[64] = {false};
@@ -1045,14 +1467,15 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
   return check_launch("mlp_tc_fwd_kernel");
 }
 
-// Which fused backward runs: the warp-specialised kernel (default) or the single-role one (PN_FIELD_BWD=v1).
-static bool bwd_ws_enabled() {
-  static int ws = -1;
-  if (ws < 0) {
+// Which fused backward runs (PN_FIELD_BWD): "v3" three-role kernel with a dedicated MMA warp (default), "ws" two-role
+// kernel, "v1" single-role kernel.
+static int bwd_variant() {
+  static int v = -1;
+  if (v < 0) {
     const char *e = getenv("PN_FIELD_BWD");
-    ws = (e && (e[0] == 'v' || e[0] == '0')) ? 0 : 1;
+    v = !e ? 2 : ((e[0] == 'v' && e[1] == '1') ? 0 : (e[0] == 'w' ? 1 : 2));
   }
-  return ws != 0;
+  return v;
 }
 
 static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const float *dout, float *dfeat,
@@ -1065,13 +1488,17 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
     cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_F32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
   const int64_t cap = (int64_t)sm_count() * 2;          // 2 CTAs/SM: 2 x 256 TMEM columns, 2 x 107 KB smem
   const int blocks = (int)(tiles < cap ? tiles : cap);
-  if (fused && bwd_ws_enabled())
+  if (fused && bwd_variant() == 2) {
+    PN_REQUIRE(A.C == 7 || ((uintptr_t)dout & 15) == 0, PN_EINVAL, "dout must be 16-byte aligned");
+    field_bwd3_kernel<<<blocks, kV3Threads, smem, st>>>(A, F, dout, dw);
+  } else if (fused && bwd_variant() == 1)
     mlp_tc_bwd_kernel<SRC_TILE, true><<<blocks, kWsThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
   else if (fused)
     mlp_tc_bwd_kernel<SRC_TILE, false><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
@@ -1123,10 +1550,19 @@ static int fill_field(FieldArgs &F, const pn_hash_grid *grid, const float *const
     F.T.t[l] = tables ? reinterpret_cast<const float2 *>(tables[l]) : nullptr;
     F.D.t[l] = dtables ? reinterpret_cast<float2 *>(dtables[l]) : nullptr;
     PN_REQUIRE(!tables || tables[l], PN_EINVAL, "tables[%d] is NULL", l);
-    PN_REQUIRE(!dtables || dtables[l], PN_EINVAL, "dtables[%d] is NULL", l);
+    PN_REQUIRE(!dtables || (dtables[l] && ((uintptr_t)dtables[l] & 15) == 0), PN_EINVAL,
+               "dtables[%d] is NULL or not 16-byte aligned", l);
   }
   F.pts = pts;
   F.qparams = qparams;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char *e = getenv("PN_DEBUG_FLAGS");
+    dbg = e ? atoi(e) : 0;
+  }
+  F.debug = dbg;
+  F.tlog = g_tlog_buf;
+  F.tlog_cap = g_tlog_cap;
   return 0;
 }
 

@@ -142,6 +142,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (all 32 lanes must execute it)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a warp-uniform value (the compiler keeps what derives from it on the uniform datapath)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// bring `bytes` (multiple of 16) starting at a 16-byte aligned global address into L2, asynchronously
+__device__ __forceinline__ void prefetch_l2(const void *gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 // named barrier over a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
 template <int ID, int THREADS>
 __device__ __forceinline__ void named_bar_sync() {

@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE — loader for the *unmodified* PocketNeRF reference.
 
-Only usable where ``/root/reference`` exists (the build container; never the GPU
-box).  It is used by ``oracle/make_golden.py`` to produce the committed golden
-vectors under ``tests/golden/`` and by the optional live cross-check tests.
-Nothing in the product package imports this file.
+Imports the reference from ``/root/reference/PocketNeRF`` (the build container) or, where that does not exist
+(the GPU box), from the verbatim copy ``oracle/_ref/PocketNeRF`` that ``oracle/build_ref.py`` makes and that ships
+with a gpurun snapshot (git-ignored, never in history).  It is used by ``oracle/make_golden.py`` to produce the
+committed golden vectors under ``tests/golden/``, by the live cross-check tests and by ``oracle/ref_train_step.py``
+(the reference arm of ``bench.py``).  Nothing in the product package imports this file.
 
 The reference cannot be imported as-is: it needs kornia, creates a
 CUDA tensor at import (utils.py:9-10), imports imageio/matplotlib/configargparse/
@@ -18,7 +19,20 @@ import sys
 import types
 from unittest import mock
 
-REF_ROOT = os.environ.get("POCKETNERF_REFERENCE", "/root/reference/PocketNeRF")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    env = os.environ.get("POCKETNERF_REFERENCE")
+    if env:
+        return env
+    for cand in ("/root/reference/PocketNeRF", os.path.join(_HERE, "_ref", "PocketNeRF")):
+        if os.path.isfile(os.path.join(cand, "hash_encoding.py")):
+            return cand
+    return "/root/reference/PocketNeRF"
+
+
+REF_ROOT = _find_root()
 
 
 def available():

@@ -15,13 +15,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = [("v1", "8", "v1"), ("ws", "8", "ws"), ("ws", "4", "ws")]
+# (PN_FIELD_FWD, PN_FWD_GW, PN_FIELD_BWD, PN_DEBUG_FLAGS, extra args)
+VARIANTS = [("v1", "8", "v1", "0", []), ("v1", "8", "ws", "0", []), ("v1", "8", "v3", "0", []),
+            ("v1", "8", "v1", "0", ["--density", "0.3"]), ("v1", "8", "ws", "0", ["--density", "0.3"]),
+            ("v1", "8", "v3", "0", ["--density", "0.3"]), ("v1", "8", "v3", "1", [])]
 
 
 def sweep(extra):
-    for fwd, gw, bwd in VARIANTS:
-        env = dict(os.environ, PN_FIELD_FWD=fwd, PN_FWD_GW=gw, PN_FIELD_BWD=bwd)
-        r = subprocess.run(["timeout", "300", sys.executable, os.path.abspath(__file__)] + extra, env=env,
+    for fwd, gw, bwd, dbg, more in VARIANTS:
+        env = dict(os.environ, PN_FIELD_FWD=fwd, PN_FWD_GW=gw, PN_FIELD_BWD=bwd, PN_DEBUG_FLAGS=dbg)
+        r = subprocess.run(["timeout", "300", sys.executable, os.path.abspath(__file__)] + list(extra) + more, env=env,
                            capture_output=True, text=True)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps({"error": r.stderr[-600:], "rc": r.returncode})
         print(line, flush=True)
@@ -33,6 +36,9 @@ def main():
     ap.add_argument("--normals", action="store_true")
     ap.add_argument("--rays", type=int, default=65536)
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--density", type=float, default=1.0, help="fraction of 16-sample blocks with a non-zero cotangent")
+    ap.add_argument("--iters", type=int, default=13)
+    ap.add_argument("--only", type=int, default=0, help="run only this samples-per-ray value (192 or 64)")
     a = ap.parse_args()
     if a.sweep:
         return sweep([x for x in sys.argv[1:] if x != "--sweep"])
@@ -52,14 +58,14 @@ def main():
     rays, _ = synthetic.ray_batch(scene, a.rays, seed=5, device=dev)
     vd = rays[1] / rays[1].norm(dim=-1, keepdim=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    out = {"variant": {k: os.environ.get(k) for k in ("PN_FIELD_FWD", "PN_FWD_GW", "PN_FIELD_BWD")}, "log2T": a.log2T,
-           "normals": a.normals}
-    for S in (192, 64):
+    out = {"variant": {k: os.environ.get(k) for k in ("PN_FIELD_FWD", "PN_FWD_GW", "PN_FIELD_BWD", "PN_DEBUG_FLAGS")},
+           "log2T": a.log2T, "normals": a.normals, "density": a.density}
+    for S in ((a.only,) if a.only else (192, 64)):
         z = torch.sort(2.0 + 4.0 * torch.rand(a.rays, S, device=dev), -1)[0]
         pts = ops.make_points(rays[0], rays[1], z)
         fw, bw = [], []
         chk = None
-        for it in range(13):
+        for it in range(a.iters):
             for prm in list(emb.parameters()) + list(net.parameters()):
                 prm.grad = None
             ops.table_grad_buffer(list(emb.tables()))        # the zeroing of the flat gradient stays outside the timing
@@ -69,7 +75,11 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             fw.append(e0.elapsed_time(e1))
-            dout = torch.ones_like(o) if it == 0 else dout
+            if it == 0:
+                dout = torch.ones_like(o)
+                if a.density < 1.0:
+                    blk = (torch.rand(a.rays, S // 16, 1, device=dev) < a.density).float()
+                    dout = dout * blk.repeat_interleave(16, 1)
             torch.cuda.synchronize()
             e0.record()
             o.backward(dout)
@@ -82,7 +92,7 @@ def main():
                        "g0_abs": float(g.double().abs().sum()), "g15_abs": float(emb.embeddings[15].weight.grad.double().abs().sum()),
                        "ds0_abs": float(net.sigma_net[0].weight.grad.double().abs().sum())}
         import numpy as np
-        out["S%d" % S] = {"points": a.rays * S, "fwd_ms": float(np.median(fw[3:])), "bwd_ms": float(np.median(bw[3:])), "check": chk}
+        out["S%d" % S] = {"points": a.rays * S, "fwd_ms": float(np.median(fw[min(3, a.iters - 1):])), "bwd_ms": float(np.median(bw[min(3, a.iters - 1):])), "check": chk}
     print(json.dumps(out))
 
 
