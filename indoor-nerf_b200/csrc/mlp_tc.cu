@@ -135,7 +135,7 @@ struct FieldArgs {
   uint4 *featb;         // bf16 feature tiles, 8 KB per 128-point tile, tile layout (forward writes, backward reads)
   int scatter_split;    // backward: half 0 scatters levels [0, split), half 1 the rest
   int debug;            // PN_DEBUG_FLAGS (measurement only): 1 = skip the scatter work, 2 = skip the gather work
-  long long *tlog;      // pn_debug_timeline buffer: [2 threads][tlog_cap] clock64 marks, or NULL
+  long long *tlog;      // pn_debug_timeline buffer: [3 threads][tlog_cap] clock64 marks, or NULL
   int tlog_cap;
   PackedDev PK;         // SRC_PACKED: tables as integer codes (inference)
 };
@@ -311,7 +311,9 @@ packed_gather8<false>(F->PK, l, F->G, c, e0, e1);
 }
 
 // epilogue of a 64-wide hidden layer, this thread's 32 columns: TMEM -> ReLU -> (fake-quant) -> bf16 tile row;
-// returns the ReLU mask of those columns
+// returns the ReLU mask of those columns.  The activation fake-quant (IEEE division, ~40 instructions per element) sits
+// behind ONE branch: written as `if (qrow)` per element it was if-converted, and the clock64 timeline showed the first
+// epilogue of every tile taking 2.4-2.8 k cycles (the others 0.2-0.6 k) with quantisation off.
 __device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, int p, int half, const float *qrow) {
   uint32_t mask = 0;
   float v[32];
@@ -323,7 +325,12 @@ __device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, 
     const bool pos = v[j] > 0.f;
     if (pos) mask |= (1u << j);
     v[j] = pos ? v[j] : 0.f;
-    if (qrow) v[j] = fake_quant(v[j], qrow[0], qrow[1], qrow[2], qrow[3], qrow[4], qrow[6] != 0.f);
+  }
+  if (qrow != nullptr) {
+    const float scale = qrow[0], denom = qrow[1], zp = qrow[2], qmin = qrow[3], qmax = qrow[4];
+    const bool train_form = qrow[6] != 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fake_quant(v[j], scale, denom, zp, qmin, qmax, train_form);
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) st_chunk(tile, chunk_off(p, half * 4 + c, 8), v + 8 * c);
@@ -1104,7 +1111,10 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     const bool lead = elect_one();
     uint32_t pr = 0, n = 0;
     bool first = true;
+    TLog T = {nullptr, 0, F.tlog_cap};
+    if (F.tlog && blockIdx.x == 0 && lead) T.p = F.tlog + 2 * F.tlog_cap;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      T.mark();
       // next tile's inputs -> L2 (saved feature tile 8 KB, cotangent rows, positions, keep flags)
       const int64_t nt = tile + gridDim.x;
       if (lead && nt < n_tiles) {
@@ -1118,17 +1128,21 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
 #define PN_MMA_ROUND(...)                                         \
   do {                                                            \
     mbar_wait(&ready, pr); pr ^= 1; fence_after_sync();           \
+    T.mark();                                                     \
     if (lead) { __VA_ARGS__; mma_commit(&done); }                 \
+    T.mark();                                                     \
     __syncwarp();                                                 \
   } while (0)
       // R1 (D1 still holds the previous tile's dX until the scatter warps have taken it)
       mbar_wait(&ready, pr); pr ^= 1;
       if (n > 0) mbar_wait(&dx_empty, (n - 1) & 1);
       fence_after_sync();
+      T.mark();
       if (lead) {
         issue3(tmem + TM_D1, k_major(sm + TS::A0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
         mma_commit(&done);
       }
+      T.mark();
       __syncwarp();
       PN_MMA_ROUND(issue3(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false));
       PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::CIN, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
@@ -1201,9 +1215,12 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   }
   float g_n2 = 0.f, g_n0[4] = {0.f, 0.f, 0.f, 0.f};
   bool first = true;
+  TLog T = {nullptr, 0, F.tlog_cap};
+  if (F.tlog && blockIdx.x == 0 && (tid == 0 || tid == 160)) T.p = F.tlog + (tid ? F.tlog_cap : 0);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kTcTile;
     const bool valid = base + p < A.in.n_points;
+    T.mark();
     // the previous tile's B5 (reader of A0 / A1) was waited for at the end of the previous iteration
     tc_load_inputs<SRC_TILE>(sm, A, &F, tile, base, p, half, valid);
     float d_o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1218,13 +1235,17 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
         if (A.in.keep && A.in.keep[base + p] == 0) d_o[6] = 0.f;
       }
     }
+    T.mark();
     epi_arrive(&ready, lane);
     // E1: H1 = relu(D1) -> A1
     epi_wait(&done, ph);
+    T.mark();
     const uint32_t h1_mask = epi_hidden32(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
+    T.mark();
     epi_arrive(&ready, lane);
     // E2: [sigma, geo] -> CIN[16..32)
     epi_wait(&done, ph);
+    T.mark();
     if (half == 0) {
       float v[17];
       tmem_ld16(lane_addr + TM_D2, v);
@@ -1233,9 +1254,11 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       st_chunk(sm + TS::CIN, chunk_off(p, 2, 4), v + 1);
       st_chunk(sm + TS::CIN, chunk_off(p, 3, 4), v + 9);
     }
+    T.mark();
     epi_arrive(&ready, lane);
     // E3: colour hidden 1 -> A1C ; (normals) NH
     epi_wait(&done, ph);
+    T.mark();
     epi_hidden32(lane_addr + TM_D1, sm + TS::A1C, p, half, nullptr);
     if (A.normals) {
       const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + half * 16;
@@ -1247,9 +1270,11 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       st_chunk(sm + TS::NH, chunk_off(p, half * 2, 4), v);
       st_chunk(sm + TS::NH, chunk_off(p, half * 2 + 1, 4), v + 8);
     }
+    T.mark();
     epi_arrive(&ready, lane);
     // E4: colour hidden 2 -> A2C ; raw normal ; B0: cotangent tiles
     epi_wait(&done, ph);
+    T.mark();
     float nraw[3] = {0.f, 0.f, 0.f};
     if (A.normals && half == 0) {
       const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + 32;
@@ -1277,6 +1302,7 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
         st_chunk(sm + TS::DNR, chunk_off(p, 1, 2), z);
       }
     }
+    T.mark();
     epi_arrive(&ready, lane);
     // normal head weight gradients on the CUDA cores (611 numbers): every row of NH / DNR must be written first
     if (A.normals) {
@@ -1291,6 +1317,7 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     }
     // E(B1): dA2pre -> A2C (in place, masked) ; (normals) dNHpre -> NH
     epi_wait(&done, ph);
+    T.mark();
     if (A.normals) mlp_sync();                     // all NH reads above are done
     epi_grad32(lane_addr + TM_D1, sm + TS::A2C, p, half, false, 0);
     if (A.normals) {
@@ -1306,6 +1333,7 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
         st_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), v + 8 * c);
       }
     }
+    T.mark();
     epi_arrive(&ready, lane);
     if (A.normals) {
       mlp_sync();                                  // dNHpre rows of every thread are written
@@ -1321,10 +1349,13 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     }
     // E(B2): dA1pre -> A1C
     epi_wait(&done, ph);
+    T.mark();
     epi_grad32(lane_addr + TM_D1, sm + TS::A1C, p, half, false, 0);
+    T.mark();
     epi_arrive(&ready, lane);
     // E(B3): [dsigma, dgeo] -> DH2
     epi_wait(&done, ph);
+    T.mark();
     if (half == 1) {
       float g[17];
       tmem_ld16(lane_addr + TM_D1 + 16, g + 1);        // dCIN[16..32) = dgeo[0..15) + pad
@@ -1340,13 +1371,17 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       st_chunk(sm + TS::DH2, chunk_off(p, 0, 2), g);
       st_chunk(sm + TS::DH2, chunk_off(p, 1, 2), g + 8);
     }
+    T.mark();
     epi_arrive(&ready, lane);
     // E(B4): dH1pre -> A1
     epi_wait(&done, ph);
+    T.mark();
     epi_grad32(lane_addr + TM_D1, sm + TS::A1, p, half, true, h1_mask);
+    T.mark();
     epi_arrive(&ready, lane);
     // B5 reads A1 and A0: wait for it before the next tile's inputs overwrite them
     epi_wait(&done, ph);
+    T.mark();
     first = false;
   }
   // flush the weight gradients (every MMA has completed: the last commit was waited on)
