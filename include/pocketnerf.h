@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 8
+#define PN_ABI_VERSION 9
 #define PN_MAX_LEVELS 16
 
 #define PN_EINVAL (-1)   /* bad argument */
@@ -163,13 +163,18 @@ int pn_field_fwd_bf16(const pn_hash_grid *grid, const float *const *tables, cons
                       const pn_mlp_weights *w, const float *pts, const float *dirs, int samples_per_ray,
                       const float *act_q, int64_t n_points, float *out, uint8_t *keep, void *feat_tiles,
                       pn_stream_t stream);
-/* Backward of pn_field_fwd_bf16 as ONE kernel: NeRFSmall backward on the saved feature tiles and, from its
- * epilogue, the run-aggregated scatter-add of the feature gradient into dtables (caller-zeroed, accumulated);
- * weight gradients accumulated into dw.  The [P,32] feature gradient never reaches HBM. */
+/* Backward of pn_field_fwd_bf16 as ONE kernel: NeRFSmall backward on the saved feature tiles and, in the same launch,
+ * the run-aggregated scatter-add of the feature gradient into dtables (caller-zeroed, accumulated, 16-byte aligned);
+ * weight gradients accumulated into dw.  The [P,32] feature gradient never reaches HBM as a tensor: the kernel's MLP
+ * warps hand each 128-point tile of it to the kernel's scatter warps through a small per-CTA ring in `workspace`
+ * (caller-owned scratch of pn_field_bwd_workspace_bytes() bytes, 16-byte aligned, contents undefined before and
+ * after; it stays L2-resident).  dout must be 16-byte aligned when the network has 4 output channels. */
 int pn_field_bwd_bf16(const pn_hash_grid *grid, float *const *dtables, const pn_mlp_weights *w,
                       const void *feat_tiles, const float *pts, const float *dirs, int samples_per_ray,
                       const float *act_q, const uint8_t *keep, const float *dout, int64_t n_points,
-                      const pn_mlp_grads *dw, pn_stream_t stream);
+                      const pn_mlp_grads *dw, void *workspace, int64_t workspace_bytes, pn_stream_t stream);
+/* Scratch size pn_field_bwd_bf16 needs on the current device (depends on its SM count only). */
+int64_t pn_field_bwd_workspace_bytes(void);
 
 /* Diagnostic: one tcgen05 GEMM with caller-chosen shared-memory descriptor fields (cfg[15], see
  * mlp_tc.cu) — proves the K-major / MN-major operand readings and the TMEM accumulator layouts on the

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpocketnerf.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_LEVELS = 16
 QROW = 8
 
@@ -58,7 +58,7 @@ _SIGNATURES = {
                         ctypes.POINTER(MlpWeights), _P],
     "pn_field_fwd_bf16": [ctypes.POINTER(HashGrid), _P, _P, ctypes.POINTER(MlpWeights), _P, _P, _I, _P, _L, _P, _P, _P, _P],
     "pn_field_bwd_bf16": [ctypes.POINTER(HashGrid), _P, ctypes.POINTER(MlpWeights), _P, _P, _P, _I, _P, _P, _P, _L,
-                          ctypes.POINTER(MlpWeights), _P],
+                          ctypes.POINTER(MlpWeights), _P, _L, _P],
     "pn_tc_selftest": [_P, _P, _P, _P, _P],
     "pn_debug_timeline": [_P, _L],
     "pn_tv_loss_fwd": [_P, _I, _I, _P, _P, _P, _P],
@@ -91,9 +91,13 @@ _OPTIONAL = {}
 _lib = None
 
 
+# entry points that do not return an error code
+_PLAIN = {"pn_field_bwd_workspace_bytes": ([], ctypes.c_int64)}
+
+
 def exported_symbols():
     """Names every build of the library must export (tests check them against include/pocketnerf.h)."""
-    return ["pn_abi_version", "pn_last_error", "pn_launch_count"] + sorted(_SIGNATURES)
+    return ["pn_abi_version", "pn_last_error", "pn_launch_count"] + sorted(_SIGNATURES) + sorted(_PLAIN)
 
 
 def register_optional(name, argtypes):
@@ -122,6 +126,9 @@ def lib():
                 continue
             fn = getattr(l, name)
             fn.argtypes, fn.restype = argtypes, ctypes.c_int
+        for name, (argtypes, restype) in _PLAIN.items():
+            fn = getattr(l, name)
+            fn.argtypes, fn.restype = argtypes, restype
         _lib = l
     return _lib
 

@@ -1410,6 +1410,335 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   if (warp == 0) tmem_dealloc(tmem, TM_BWD_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Fused backward, fourth structure (pn_field_bwd_bf16 default): the v3 roles with the scatter DECOUPLED from the
+// round chain through a small ring in global memory (L2-resident: kRingSlots x 16 KB per CTA).
+//   warps 0-7   epilogue; after B5 each thread copies its half row of dX (TMEM, fp32) into the CTA's ring slot
+//   warp  8     MMA issuer (as v3)
+//   warps 9-15  scatter: 7 warps take (tile, quarter) items round-robin from the ring — any warp can take any quarter
+//               (the TMEM lane-quarter rule no longer applies), and they may lag the chain by kRingSlots tiles.
+// Why: with the training step's own gradients nearly every warp of 32 samples has some non-zero rows, so the scatter
+// costs its full ~230 instructions per level per warp; 4 scatter warps tied to the chain by a one-tile TMEM hand-off
+// (v3) took ~30 k cycles per tile against ~13 k for the chain.  What the scatter needs is issue slots from many warps
+// (the standalone scatter kernel reaches 71 % issue utilisation with 32 warps/SM), not a place in the chain.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kV4ScatterWarps = 7;
+constexpr int kV4Threads = kTcThreads + 32 + 32 * kV4ScatterWarps;      // 512
+constexpr int kV4EpiRegs = 80, kV4AuxRegs = 48;                         // 256*80 + 256*48 = 512*64 (launch bound at 2 CTAs/SM)
+constexpr int kRingSlots = 4;
+static_assert(kV4Threads == 512, "register budget assumes 16 warps");
+
+__global__ void __launch_bounds__(kV4Threads, 2)
+field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout, const pn_mlp_grads G,
+                  float *__restrict__ ring) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t ready, done, ring_full[kRingSlots], ring_empty[kRingSlots];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = uniform_warp_idx();
+  load_all_weights(sm, A);
+  if (warp == 0) tmem_alloc(&tmem_slot, TM_BWD_COLS);
+  if (tid == 0) {
+    mbar_init(&ready, 8); mbar_init(&done, 1);
+    for (int i = 0; i < kRingSlots; ++i) { mbar_init(&ring_full[i], 8); mbar_init(&ring_empty[i], 4); }
+    mbar_fence_init();
+  }
+  fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
+  const int C = A.C;
+
+  float *const cta_ring = ring + (size_t)blockIdx.x * (kRingSlots * kTcTile * 32);
+  if (warp >= 8) setmaxnreg_dec<kV4AuxRegs>();        // both warpgroups 8-11 and 12-15, one instruction
+  if (warp == 8) {
+    // ---------------- MMA role ----------------
+    const bool lead = elect_one();
+    uint32_t pr = 0, n = 0;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      // next tile's inputs -> L2 (saved feature tile 8 KB, cotangent rows, positions, keep flags)
+      const int64_t nt = tile + gridDim.x;
+      if (lead && nt < n_tiles) {
+        const int64_t nb = nt * kTcTile;
+        const int64_t rows = (A.in.n_points - nb) < kTcTile ? (A.in.n_points - nb) : kTcTile;
+        prefetch_l2(F.featb + nt * 512, 8192);
+        const uint32_t db = (uint32_t)(rows * C * 4) & ~15u, pb = (uint32_t)(rows * 12) & ~15u;
+        if (db && (((uintptr_t)(dout + nb * C)) & 15) == 0) prefetch_l2(dout + nb * C, db);
+        if (pb && (((uintptr_t)(F.pts + nb * 3)) & 15) == 0) prefetch_l2(F.pts + nb * 3, pb);
+      }
+#define PN_MMA_ROUND(...)                                         \
+  do {                                                            \
+    mbar_wait(&ready, pr); pr ^= 1; fence_after_sync();           \
+    if (lead) { __VA_ARGS__; mma_commit(&done); }                 \
+    __syncwarp();                                                 \
+  } while (0)
+      PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::A0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false));
+      PN_MMA_ROUND(issue3(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false));
+      PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::CIN, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
+                   if (A.normals) issue3(tmem + TM_DN, k_major(sm + TS::CIN, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false));
+      PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), k_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 0), 4, false);
+                   if (A.normals) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false));
+      // B1: dC2^T += A2c^T dOut ; dA2 = dOut C2 ; (normals) dNH = dNraw N2
+      PN_MMA_ROUND(issue3(tmem + TM_GC2, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::DOUT, 16), instr_desc(64, 16, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::DOUT, 16), mn_major(sm + TS::W_C2, 64), instr_desc(128, 64, 0, 1), 1, false);
+                   if (A.normals) issue3(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false));
+      // B2: dC1 += dA2pre^T A1c ; dA1 = dA2pre C1
+      PN_MMA_ROUND(issue3(tmem + TM_GC1, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::A1C, 64), instr_desc(64, 64, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::A2C, 64), mn_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 1), 4, false));
+      // B3: dC0 += dA1pre^T CIN ; dCIN = dA1pre C0 ; (normals) dgeo_n = dNHpre N0
+      PN_MMA_ROUND(issue3(tmem + TM_GC0, mn_major(sm + TS::A1C, 64), mn_major(sm + TS::CIN, 32), instr_desc(64, 32, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), mn_major(sm + TS::W_C0, 32), instr_desc(128, 32, 0, 1), 4, false);
+                   if (A.normals) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false));
+      // B4: dS1^T += H1^T dH2 ; dH1 = dH2 S1
+      PN_MMA_ROUND(issue3(tmem + TM_GS1, mn_major(sm + TS::A1, 64), mn_major(sm + TS::DH2, 16), instr_desc(64, 16, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::DH2, 16), mn_major(sm + TS::W_S1, 64), instr_desc(128, 64, 0, 1), 1, false));
+      // B5: dS0 += dH1pre^T X ; dX = dH1pre S0
+      PN_MMA_ROUND(issue3(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
+                   issue3(tmem + TM_D1, k_major(sm + TS::A1, 64), mn_major(sm + TS::W_S0, 32), instr_desc(128, 32, 0, 1), 4, false));
+#undef PN_MMA_ROUND
+      first = false;
+    }
+    __syncthreads();
+    return;
+  }
+
+  if (warp >= 9) {
+    // ---------------- scatter role: kV4ScatterWarps warps, work item = (tile, quarter), taken round-robin ----------------
+    const int sw = warp - 9;
+    const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;      // tiles this CTA walks
+    for (int64_t item = sw; item < my_tiles * 4; item += kV4ScatterWarps) {
+      const int64_t n = item >> 2;
+      const int qd = (int)(item & 3), slot = (int)(n % kRingSlots);
+      const int64_t pt = (blockIdx.x + n * gridDim.x) * kTcTile + qd * 32 + lane;
+      const bool valid = pt < A.in.n_points;
+      float xv[3] = {0.f, 0.f, 0.f};
+      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
+      mbar_wait(&ring_full[slot], (uint32_t)(n / kRingSlots) & 1);
+      float g[32];                                   // indexed by the rolled level loop -> local memory (L1-resident)
+      const float4 *row = reinterpret_cast<const float4 *>(cta_ring + ((size_t)slot * kTcTile + qd * 32 + lane) * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = row[j];                     // plain (coherent) loads: written by this CTA's epilogue warps
+        g[4 * j] = v.x; g[4 * j + 1] = v.y; g[4 * j + 2] = v.z; g[4 * j + 3] = v.w;
+      }
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) any = any || (g[j] != 0.f);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ring_empty[slot]);
+      if (!__any_sync(0xffffffffu, valid && any) || (F.debug & 1)) continue;     // 32 samples without a gradient
+#pragma unroll 1
+      for (int l = 0; l < F.G.n_levels; ++l)
+        scatter_level<false>(F.G, F.D.t[l], l, xv, valid ? g[2 * l] : 0.f, valid ? g[2 * l + 1] : 0.f, lane);
+    }
+    __syncthreads();
+    return;
+  }
+
+  // ---------------- epilogue role ----------------
+  setmaxnreg_inc<kV4EpiRegs>();
+  const int p = tid & 127, half = tid >> 7;
+  uint32_t ph = 0;
+  float q[8];
+  const float *qrow = nullptr;
+  if (A.in.act_q) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
+    if (q[5] != 0.f) qrow = q;
+  }
+  float g_n2 = 0.f, g_n0[4] = {0.f, 0.f, 0.f, 0.f};
+  bool first = true;
+  uint32_t n_done = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kTcTile;
+    const bool valid = base + p < A.in.n_points;
+    // the previous tile's B5 (reader of A0 / A1) was waited for at the end of the previous iteration
+    tc_load_inputs<SRC_TILE>(sm, A, &F, tile, base, p, half, valid);
+    float d_o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      if (C == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(dout + (base + p) * 4));
+        d_o[0] = v.x; d_o[1] = v.y; d_o[2] = v.z; d_o[3] = v.w;
+        if (A.in.keep && A.in.keep[base + p] == 0) d_o[3] = 0.f;                  // run_nerf.py:66
+      } else {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) d_o[c] = __ldg(dout + (base + p) * 7 + c);
+        if (A.in.keep && A.in.keep[base + p] == 0) d_o[6] = 0.f;
+      }
+    }
+    epi_arrive(&ready, lane);
+    // E1: H1 = relu(D1) -> A1
+    epi_wait(&done, ph);
+    const uint32_t h1_mask = epi_hidden32(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
+    epi_arrive(&ready, lane);
+    // E2: [sigma, geo] -> CIN[16..32)
+    epi_wait(&done, ph);
+    if (half == 0) {
+      float v[17];
+      tmem_ld16(lane_addr + TM_D2, v);
+      tmem_ld_wait();
+      v[16] = 0.f;
+      st_chunk(sm + TS::CIN, chunk_off(p, 2, 4), v + 1);
+      st_chunk(sm + TS::CIN, chunk_off(p, 3, 4), v + 9);
+    }
+    epi_arrive(&ready, lane);
+    // E3: colour hidden 1 -> A1C ; (normals) NH
+    epi_wait(&done, ph);
+    epi_hidden32(lane_addr + TM_D1, sm + TS::A1C, p, half, nullptr);
+    if (A.normals) {
+      const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + half * 16;
+      float v[16];
+      tmem_ld16(lane_addr + TM_DN + half * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + bias[j], 0.f);
+      st_chunk(sm + TS::NH, chunk_off(p, half * 2, 4), v);
+      st_chunk(sm + TS::NH, chunk_off(p, half * 2 + 1, 4), v + 8);
+    }
+    epi_arrive(&ready, lane);
+    // E4: colour hidden 2 -> A2C ; raw normal ; B0: cotangent tiles
+    epi_wait(&done, ph);
+    float nraw[3] = {0.f, 0.f, 0.f};
+    if (A.normals && half == 0) {
+      const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + 32;
+      float v[16];
+      tmem_ld16(lane_addr + TM_D2, v);
+      tmem_ld_wait();
+      nraw[0] = v[0] + bias[0]; nraw[1] = v[1] + bias[1]; nraw[2] = v[2] + bias[2];
+    }
+    epi_hidden32(lane_addr + TM_D1, sm + TS::A2C, p, half, nullptr);
+    if (half == 0) {
+      float v[8] = {d_o[0], d_o[1], d_o[2], 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      st_chunk(sm + TS::DOUT, chunk_off(p, 0, 2), v);
+      st_chunk(sm + TS::DOUT, chunk_off(p, 1, 2), z);
+      if (A.normals) {
+        const float nn = sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]);
+        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (nn > 1e-12f) {
+          const float m0 = nraw[0] / nn, m1 = nraw[1] / nn, m2 = nraw[2] / nn;
+          const float dot = m0 * d_o[4] + m1 * d_o[5] + m2 * d_o[6];
+          r[0] = (d_o[4] - m0 * dot) / nn; r[1] = (d_o[5] - m1 * dot) / nn; r[2] = (d_o[6] - m2 * dot) / nn;
+        } else {
+          r[0] = d_o[4] / 1e-12f; r[1] = d_o[5] / 1e-12f; r[2] = d_o[6] / 1e-12f;
+        }
+        st_chunk(sm + TS::DNR, chunk_off(p, 0, 2), r);
+        st_chunk(sm + TS::DNR, chunk_off(p, 1, 2), z);
+      }
+    }
+    epi_arrive(&ready, lane);
+    // normal head weight gradients on the CUDA cores (611 numbers): every row of NH / DNR must be written first
+    if (A.normals) {
+      mlp_sync();
+      if (tid < 99) {
+        const int j = tid < 96 ? tid >> 5 : tid - 96, k = tid & 31;
+        float s = 0.f;
+        for (int r = 0; r < kTcTile; ++r)
+          s += tile_elem(sm + TS::DNR, r, j, 2) * (tid < 96 ? tile_elem(sm + TS::NH, r, k, 4) : 1.f);
+        g_n2 += s;
+      }
+    }
+    // E(B1): dA2pre -> A2C (in place, masked) ; (normals) dNHpre -> NH
+    epi_wait(&done, ph);
+    if (A.normals) mlp_sync();                     // all NH reads above are done
+    epi_grad32(lane_addr + TM_D1, sm + TS::A2C, p, half, false, 0);
+    if (A.normals) {
+      float v[16];
+      tmem_ld16(lane_addr + TM_DN + half * 16, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float a[8];
+        ld_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * c + j] = a[j] > 0.f ? v[8 * c + j] : 0.f;
+        st_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), v + 8 * c);
+      }
+    }
+    epi_arrive(&ready, lane);
+    if (A.normals) {
+      mlp_sync();                                  // dNHpre rows of every thread are written
+      if (tid < 128) {                             // dN0w[j][k] (k < 15) and dN0b[j] (k == 15): 4 outputs per thread
+        const int j = tid >> 2, k0 = (tid & 3) * 4;
+        for (int r = 0; r < kTcTile; ++r) {
+          const float d = tile_elem(sm + TS::NH, r, j, 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            g_n0[i] += d * ((k0 + i) < 15 ? tile_elem(sm + TS::CIN, r, 16 + k0 + i, 4) : 1.f);
+        }
+      }
+    }
+    // E(B2): dA1pre -> A1C
+    epi_wait(&done, ph);
+    epi_grad32(lane_addr + TM_D1, sm + TS::A1C, p, half, false, 0);
+    epi_arrive(&ready, lane);
+    // E(B3): [dsigma, dgeo] -> DH2
+    epi_wait(&done, ph);
+    if (half == 1) {
+      float g[17];
+      tmem_ld16(lane_addr + TM_D1 + 16, g + 1);        // dCIN[16..32) = dgeo[0..15) + pad
+      tmem_ld_wait();
+      if (A.normals) {
+        float v[16];
+        tmem_ld16(lane_addr + TM_D2, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 15; ++j) g[1 + j] += v[j];
+      }
+      g[0] = d_o[3];                                   // dsigma (keep mask applied above when C == 4)
+      st_chunk(sm + TS::DH2, chunk_off(p, 0, 2), g);
+      st_chunk(sm + TS::DH2, chunk_off(p, 1, 2), g + 8);
+    }
+    epi_arrive(&ready, lane);
+    // E(B4): dH1pre -> A1
+    epi_wait(&done, ph);
+    epi_grad32(lane_addr + TM_D1, sm + TS::A1, p, half, true, h1_mask);
+    epi_arrive(&ready, lane);
+    // B5 reads A1 and A0: wait for it before the next tile's inputs overwrite them; its dX goes to the ring slot
+    epi_wait(&done, ph);
+    {
+      const int slot = (int)(n_done % kRingSlots);
+      if (n_done >= kRingSlots) mbar_wait(&ring_empty[slot], (uint32_t)(n_done / kRingSlots - 1) & 1);
+      float v[16];
+      tmem_ld16(lane_addr + TM_D1 + half * 16, v);
+      tmem_ld_wait();
+      float4 *row = reinterpret_cast<float4 *>(cta_ring + ((size_t)slot * kTcTile + p) * 32 + half * 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      fence_before_sync();                             // the tcgen05.ld above precedes the next tile's first MMA (via `ready`)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ring_full[slot]);
+    }
+    ++n_done;
+    first = false;
+  }
+  // flush the weight gradients (every MMA has completed: the last commit was waited on)
+  if (!first && warp < 4) {
+    const bool owner = lane < 16;
+    const int row = warp * 16 + lane;
+    flush_acc(lane_addr + TM_GC1, 64, owner, row, G.c1, 64, 64, 64, false);
+    flush_acc(lane_addr + TM_GS0, 32, owner, row, G.s0, 32, 64, 32, false);
+    flush_acc(lane_addr + TM_GC0, 32, owner, row, G.c0, 31, 64, 31, false);
+    flush_acc(lane_addr + TM_GS1, 16, owner, row, G.s1, 64, 64, 16, true);
+    flush_acc(lane_addr + TM_GC2, 16, owner, row, G.c2, 64, 64, 3, true);
+  }
+  if (!first && A.normals) {
+    if (tid < 96) { if (G.n2w) atomicAdd(G.n2w + (tid >> 5) * 32 + (tid & 31), g_n2); }
+    else if (tid < 99) { if (G.n2b) atomicAdd(G.n2b + (tid - 96), g_n2); }
+    if (tid < 128) {
+      const int j = tid >> 2, k0 = (tid & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (k0 + i < 15) { if (G.n0w) atomicAdd(G.n0w + j * 15 + k0 + i, g_n0[i]); }
+        else if (G.n0b) atomicAdd(G.n0b + j, g_n0[i]);
+      }
+    }
+  }
+  fence_before_sync(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TM_BWD_COLS);
+}
+
 }  // namespace pn
 
 using namespace pn;
@@ -1502,19 +1831,22 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
   return check_launch("mlp_tc_fwd_kernel");
 }
 
-// Which fused backward runs (PN_FIELD_BWD): "v3" three-role kernel with a dedicated MMA warp (default), "ws" two-role
-// kernel, "v1" single-role kernel.
+// Which fused backward runs (PN_FIELD_BWD): "v4" three roles + ring-decoupled scatter (default), "v3" three roles with
+// the TMEM hand-off, "ws" two-role kernel, "v1" single-role kernel.
 static int bwd_variant() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("PN_FIELD_BWD");
-    v = !e ? 2 : ((e[0] == 'v' && e[1] == '1') ? 0 : (e[0] == 'w' ? 1 : 2));
+    v = !e ? 3 : ((e[0] == 'v' && e[1] == '1') ? 0 : (e[0] == 'w' ? 1 : ((e[0] == 'v' && e[1] == '3') ? 2 : 3)));
   }
   return v;
 }
+// bytes of the dX ring of the default backward: one ring of kRingSlots 128 x 32 fp32 tiles per resident CTA
+static int64_t field_bwd_workspace_bytes() { return (int64_t)sm_count() * 2 * kRingSlots * kTcTile * 32 * 4; }
 
 static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const float *dout, float *dfeat,
-                         int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads &dw, cudaStream_t st) {
+                         int64_t dfeat_stride, float *dsh, int64_t dsh_stride, const pn_mlp_grads &dw, cudaStream_t st,
+                         void *workspace = nullptr, int64_t workspace_bytes = 0) {
   const int smem = TS::BWD_END;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -1524,14 +1856,20 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
   const int64_t cap = (int64_t)sm_count() * 2;          // 2 CTAs/SM: 2 x 256 TMEM columns, 2 x 107 KB smem
   const int blocks = (int)(tiles < cap ? tiles : cap);
-  if (fused && bwd_variant() == 2) {
-    PN_REQUIRE(A.C == 7 || ((uintptr_t)dout & 15) == 0, PN_EINVAL, "dout must be 16-byte aligned");
+  if (fused && bwd_variant() >= 2) PN_REQUIRE(A.C == 7 || ((uintptr_t)dout & 15) == 0, PN_EINVAL, "dout must be 16-byte aligned");
+  if (fused && bwd_variant() == 3) {
+    PN_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= field_bwd_workspace_bytes(), PN_EINVAL,
+               "pn_field_bwd_bf16 needs a 16-byte aligned workspace of pn_field_bwd_workspace_bytes() = %lld bytes (got %lld)",
+               (long long)field_bwd_workspace_bytes(), (long long)workspace_bytes);
+    field_bwd4_kernel<<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, reinterpret_cast<float *>(workspace));
+  } else if (fused && bwd_variant() == 2) {
     field_bwd3_kernel<<<blocks, kV3Threads, smem, st>>>(A, F, dout, dw);
   } else if (fused && bwd_variant() == 1)
     mlp_tc_bwd_kernel<SRC_TILE, true><<<blocks, kWsThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
@@ -1628,7 +1966,7 @@ extern "C" int pn_field_fwd_bf16(const pn_hash_grid *grid, const float *const *t
 extern "C" int pn_field_bwd_bf16(const pn_hash_grid *grid, float *const *dtables, const pn_mlp_weights *w,
                                  const void *feat_tiles, const float *pts, const float *dirs, int samples_per_ray,
                                  const float *act_q, const uint8_t *keep, const float *dout, int64_t n_points,
-                                 const pn_mlp_grads *dw, pn_stream_t stream) {
+                                 const pn_mlp_grads *dw, void *workspace, int64_t workspace_bytes, pn_stream_t stream) {
   PN_REQUIRE(w && dtables && dirs && dout && dw && feat_tiles, PN_EINVAL, "NULL pointer argument");
   pn_mlp_input in = {};
   in.feat = pts;
@@ -1650,8 +1988,10 @@ extern "C" int pn_field_bwd_bf16(const pn_hash_grid *grid, float *const *dtables
     if (split < 1 || split > 15) split = 8;
   }
   F.scatter_split = split;
-  return launch_tc_bwd(A, F, true, dout, nullptr, 32, nullptr, 16, *dw, as_stream(stream));
+  return launch_tc_bwd(A, F, true, dout, nullptr, 32, nullptr, 16, *dw, as_stream(stream), workspace, workspace_bytes);
 }
+
+extern "C" int64_t pn_field_bwd_workspace_bytes(void) { return pn::field_bwd_workspace_bytes(); }
 
 namespace pn {
 int fill_packed(PackedDev &T, const pn_hash_grid *grid, const pn_packed_tables *packed);   // hash_encode.cu

@@ -336,6 +336,22 @@ class MlpFn(torch.autograd.Function):
         return (dx, None, None) + tuple(dw[k] for k in ctx.keys)
 
 
+_BWD_WORKSPACE = {}
+
+
+def _field_bwd_workspace(device):
+    """Scratch of the fused backward (its dX ring, see include/pocketnerf.h): one buffer per device, reused by every
+    launch — launches on one stream are ordered, and the kernel leaves nothing in it."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _BWD_WORKSPACE.get(key)
+    if buf is None:
+        with torch.cuda.device(device):
+            n = int(_lib.lib().pn_field_bwd_workspace_bytes())
+        buf = torch.empty(n, dtype=torch.uint8, device=device)
+        _BWD_WORKSPACE[key] = buf
+    return buf
+
+
 class FieldFn(torch.autograd.Function):
     """raw[P, 4|7] = FieldFn.apply(pts[P,3], viewdirs[N,3], S, grid, qparams, act_q, keys, n_tables,
     *tables, *weights): hash encode -> SH -> NeRFSmall -> keep-mask, i.e. run_network
@@ -390,9 +406,11 @@ class FieldFn(torch.autograd.Function):
             dw = {k: torch.zeros_like(w[k]) for k in _MLP_KEYS if w.get(k) is not None}
             with _guard(pts):
                 ws, gs = _weights_struct(w), _weights_struct(dw)
+                wsp = _field_bwd_workspace(pts.device)
                 call("pn_field_bwd_bf16", ctypes.byref(ctx.grid), _ptr_array(list(flat.unbind(0))), ctypes.byref(ws),
                      dptr(feat, torch.uint8), dptr(pts), dptr(dirs), int(ctx.S), dptr(ctx.act_q, allow_none=True),
-                     dptr(keep, torch.bool), dptr(dout), pts.shape[0], ctypes.byref(gs), stream())
+                     dptr(keep, torch.bool), dptr(dout), pts.shape[0], ctypes.byref(gs), dptr(wsp, torch.uint8),
+                     wsp.numel(), stream())
             return (None,) * (8 + ctx.n_tables) + tuple(dw[k] for k in ctx.keys)
         dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep, mode=ctx.mode)
         if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):
