@@ -320,12 +320,19 @@ __device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, 
   tmem_ld16(taddr + half * 32, v);
   tmem_ld16(taddr + half * 32 + 16, v + 16);
   tmem_ld_wait();
+  // four dependent shift-or chains of 8 bits: written as 32 independent `mask |= bit << j` terms, ptxas kept the terms
+  // live and spilled 24 of them to local memory (which, with 2 x 107 KB of shared memory per SM, has almost no L1)
+  uint32_t m4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const bool pos = v[j] > 0.f;
-    if (pos) mask |= (1u << j);
-    v[j] = pos ? v[j] : 0.f;
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      const bool pos = v[8 * c + j] > 0.f;
+      m4[c] = (m4[c] << 1) | (pos ? 1u : 0u);
+      v[8 * c + j] = fmaxf(v[8 * c + j], 0.f);
+    }
   }
+  mask = m4[0] | (m4[1] << 8) | (m4[2] << 16) | (m4[3] << 24);
   if (qrow != nullptr) {
     const float scale = qrow[0], denom = qrow[1], zp = qrow[2], qmin = qrow[3], qmax = qrow[4];
     const bool train_form = qrow[6] != 0.f;
@@ -1429,12 +1436,14 @@ constexpr int kV4EpiRegs = 80, kV4AuxRegs = 48;                         // 256*8
 constexpr int kRingSlots = 4;
 static_assert(kV4Threads == 512, "register budget assumes 16 warps");
 
+template <bool NORMALS>
 __global__ void __launch_bounds__(kV4Threads, 2)
 field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout, const pn_mlp_grads G,
                   float *__restrict__ ring) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t ready, done, ring_full[kRingSlots], ring_empty[kRingSlots];
+  __shared__ uint32_t ring_nz[kRingSlots][4][2];      // per slot / quarter / column half: lanes whose dX half row is non-zero
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = uniform_warp_idx();
   load_all_weights(sm, A);
@@ -1477,20 +1486,20 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::A0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false));
       PN_MMA_ROUND(issue3(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false));
       PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::CIN, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
-                   if (A.normals) issue3(tmem + TM_DN, k_major(sm + TS::CIN, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false));
+                   if (NORMALS) issue3(tmem + TM_DN, k_major(sm + TS::CIN, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false));
       PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), k_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 0), 4, false);
-                   if (A.normals) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false));
+                   if (NORMALS) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false));
       // B1: dC2^T += A2c^T dOut ; dA2 = dOut C2 ; (normals) dNH = dNraw N2
       PN_MMA_ROUND(issue3(tmem + TM_GC2, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::DOUT, 16), instr_desc(64, 16, 1, 1), 8, !first);
                    issue3(tmem + TM_D1, k_major(sm + TS::DOUT, 16), mn_major(sm + TS::W_C2, 64), instr_desc(128, 64, 0, 1), 1, false);
-                   if (A.normals) issue3(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false));
+                   if (NORMALS) issue3(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false));
       // B2: dC1 += dA2pre^T A1c ; dA1 = dA2pre C1
       PN_MMA_ROUND(issue3(tmem + TM_GC1, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::A1C, 64), instr_desc(64, 64, 1, 1), 8, !first);
                    issue3(tmem + TM_D1, k_major(sm + TS::A2C, 64), mn_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 1), 4, false));
       // B3: dC0 += dA1pre^T CIN ; dCIN = dA1pre C0 ; (normals) dgeo_n = dNHpre N0
       PN_MMA_ROUND(issue3(tmem + TM_GC0, mn_major(sm + TS::A1C, 64), mn_major(sm + TS::CIN, 32), instr_desc(64, 32, 1, 1), 8, !first);
                    issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), mn_major(sm + TS::W_C0, 32), instr_desc(128, 32, 0, 1), 4, false);
-                   if (A.normals) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false));
+                   if (NORMALS) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false));
       // B4: dS1^T += H1^T dH2 ; dH1 = dH2 S1
       PN_MMA_ROUND(issue3(tmem + TM_GS1, mn_major(sm + TS::A1, 64), mn_major(sm + TS::DH2, 16), instr_desc(64, 16, 1, 1), 8, !first);
                    issue3(tmem + TM_D1, k_major(sm + TS::DH2, 16), mn_major(sm + TS::W_S1, 64), instr_desc(128, 64, 0, 1), 1, false));
@@ -1516,22 +1525,24 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       float xv[3] = {0.f, 0.f, 0.f};
       if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
       mbar_wait(&ring_full[slot], (uint32_t)(n / kRingSlots) & 1);
-      float g[32];                                   // indexed by the rolled level loop -> local memory (L1-resident)
-      const float4 *row = reinterpret_cast<const float4 *>(cta_ring + ((size_t)slot * kTcTile + qd * 32 + lane) * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 v = row[j];                     // plain (coherent) loads: written by this CTA's epilogue warps
-        g[4 * j] = v.x; g[4 * j + 1] = v.y; g[4 * j + 2] = v.z; g[4 * j + 3] = v.w;
+      // rows of this quarter with a gradient (published by the epilogue warps with the tile); 32 gradient-free samples
+      // (empty space, occluded samples) cost one shared-memory read
+      const uint32_t rows_nz = (ring_nz[slot][qd][0] | ring_nz[slot][qd][1]) & __ballot_sync(0xffffffffu, valid);
+      if (rows_nz != 0u && !(F.debug & 1)) {
+        const bool act = (rows_nz >> lane) & 1u;
+        // two values per level straight from the ring row (L2 / L1 hits), the next level's in flight during this one's
+        // scatter: no local-memory staging (the 107 KB x 2 of shared memory leave the SM almost no L1 for stack traffic)
+        const float2 *row = reinterpret_cast<const float2 *>(cta_ring + ((size_t)slot * kTcTile + qd * 32 + lane) * 32);
+        float2 gc = act ? row[0] : make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int l = 0; l < F.G.n_levels; ++l) {
+          const float2 gn = (act && l + 1 < F.G.n_levels) ? row[l + 1] : make_float2(0.f, 0.f);
+          scatter_level<false>(F.G, F.D.t[l], l, xv, gc.x, gc.y, lane);
+          gc = gn;
+        }
       }
-      bool any = false;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) any = any || (g[j] != 0.f);
       __syncwarp();
       if (lane == 0) mbar_arrive(&ring_empty[slot]);
-      if (!__any_sync(0xffffffffu, valid && any) || (F.debug & 1)) continue;     // 32 samples without a gradient
-#pragma unroll 1
-      for (int l = 0; l < F.G.n_levels; ++l)
-        scatter_level<false>(F.G, F.D.t[l], l, xv, valid ? g[2 * l] : 0.f, valid ? g[2 * l + 1] : 0.f, lane);
     }
     __syncthreads();
     return;
@@ -1587,7 +1598,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     // E3: colour hidden 1 -> A1C ; (normals) NH
     epi_wait(&done, ph);
     epi_hidden32(lane_addr + TM_D1, sm + TS::A1C, p, half, nullptr);
-    if (A.normals) {
+    if (NORMALS) {
       const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + half * 16;
       float v[16];
       tmem_ld16(lane_addr + TM_DN + half * 16, v);
@@ -1601,7 +1612,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     // E4: colour hidden 2 -> A2C ; raw normal ; B0: cotangent tiles
     epi_wait(&done, ph);
     float nraw[3] = {0.f, 0.f, 0.f};
-    if (A.normals && half == 0) {
+    if (NORMALS && half == 0) {
       const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + 32;
       float v[16];
       tmem_ld16(lane_addr + TM_D2, v);
@@ -1613,7 +1624,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       float v[8] = {d_o[0], d_o[1], d_o[2], 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       st_chunk(sm + TS::DOUT, chunk_off(p, 0, 2), v);
       st_chunk(sm + TS::DOUT, chunk_off(p, 1, 2), z);
-      if (A.normals) {
+      if (NORMALS) {
         const float nn = sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]);
         float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (nn > 1e-12f) {
@@ -1629,7 +1640,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     }
     epi_arrive(&ready, lane);
     // normal head weight gradients on the CUDA cores (611 numbers): every row of NH / DNR must be written first
-    if (A.normals) {
+    if (NORMALS) {
       mlp_sync();
       if (tid < 99) {
         const int j = tid < 96 ? tid >> 5 : tid - 96, k = tid & 31;
@@ -1641,9 +1652,9 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     }
     // E(B1): dA2pre -> A2C (in place, masked) ; (normals) dNHpre -> NH
     epi_wait(&done, ph);
-    if (A.normals) mlp_sync();                     // all NH reads above are done
+    if (NORMALS) mlp_sync();                     // all NH reads above are done
     epi_grad32(lane_addr + TM_D1, sm + TS::A2C, p, half, false, 0);
-    if (A.normals) {
+    if (NORMALS) {
       float v[16];
       tmem_ld16(lane_addr + TM_DN + half * 16, v);
       tmem_ld_wait();
@@ -1657,7 +1668,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       }
     }
     epi_arrive(&ready, lane);
-    if (A.normals) {
+    if (NORMALS) {
       mlp_sync();                                  // dNHpre rows of every thread are written
       if (tid < 128) {                             // dN0w[j][k] (k < 15) and dN0b[j] (k == 15): 4 outputs per thread
         const int j = tid >> 2, k0 = (tid & 3) * 4;
@@ -1679,7 +1690,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       float g[17];
       tmem_ld16(lane_addr + TM_D1 + 16, g + 1);        // dCIN[16..32) = dgeo[0..15) + pad
       tmem_ld_wait();
-      if (A.normals) {
+      if (NORMALS) {
         float v[16];
         tmem_ld16(lane_addr + TM_D2, v);
         tmem_ld_wait();
@@ -1704,11 +1715,18 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       tmem_ld16(lane_addr + TM_D1 + half * 16, v);
       tmem_ld_wait();
       float4 *row = reinterpret_cast<float4 *>(cta_ring + ((size_t)slot * kTcTile + p) * 32 + half * 16);
+      bool nzr = false;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      for (int c = 0; c < 4; ++c) {
+        row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        nzr = nzr || v[4 * c] != 0.f || v[4 * c + 1] != 0.f || v[4 * c + 2] != 0.f || v[4 * c + 3] != 0.f;
+      }
+      const uint32_t nzm = __ballot_sync(0xffffffffu, nzr && valid);
       fence_before_sync();                             // the tcgen05.ld above precedes the next tile's first MMA (via `ready`)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ring_full[slot]);
+      if (lane == 0) {
+        ring_nz[slot][warp & 3][half] = nzm;
+        mbar_arrive(&ring_full[slot]);                 // release: this warp's ring stores (ordered by the ballot) and the mask
+      }
     }
     ++n_done;
     first = false;
@@ -1723,7 +1741,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     flush_acc(lane_addr + TM_GS1, 16, owner, row, G.s1, 64, 64, 16, true);
     flush_acc(lane_addr + TM_GC2, 16, owner, row, G.c2, 64, 64, 3, true);
   }
-  if (!first && A.normals) {
+  if (!first && NORMALS) {
     if (tid < 96) { if (G.n2w) atomicAdd(G.n2w + (tid >> 5) * 32 + (tid & 31), g_n2); }
     else if (tid < 99) { if (G.n2b) atomicAdd(G.n2b + (tid - 96), g_n2); }
     if (tid < 128) {
@@ -1856,7 +1874,8 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
@@ -1868,7 +1887,8 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
     PN_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= field_bwd_workspace_bytes(), PN_EINVAL,
                "pn_field_bwd_bf16 needs a 16-byte aligned workspace of pn_field_bwd_workspace_bytes() = %lld bytes (got %lld)",
                (long long)field_bwd_workspace_bytes(), (long long)workspace_bytes);
-    field_bwd4_kernel<<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, reinterpret_cast<float *>(workspace));
+    if (A.normals) field_bwd4_kernel<true><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, reinterpret_cast<float *>(workspace));
+    else field_bwd4_kernel<false><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, reinterpret_cast<float *>(workspace));
   } else if (fused && bwd_variant() == 2) {
     field_bwd3_kernel<<<blocks, kV3Threads, smem, st>>>(A, F, dout, dw);
   } else if (fused && bwd_variant() == 1)

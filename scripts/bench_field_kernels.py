@@ -16,9 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 # (PN_FIELD_FWD, PN_FWD_GW, PN_FIELD_BWD, PN_DEBUG_FLAGS, extra args)
-VARIANTS = [("v1", "8", "v1", "0", []), ("v1", "8", "ws", "0", []), ("v1", "8", "v3", "0", []),
-            ("v1", "8", "v1", "0", ["--density", "0.3"]), ("v1", "8", "ws", "0", ["--density", "0.3"]),
-            ("v1", "8", "v3", "0", ["--density", "0.3"]), ("v1", "8", "v3", "1", [])]
+VARIANTS = [("v1", "8", "v1", "0", []), ("v1", "8", "v3", "0", []), ("v1", "8", "v4", "0", []),
+            ("v1", "8", "v1", "0", ["--density", "0.1"]), ("v1", "8", "v3", "0", ["--density", "0.1"]),
+            ("v1", "8", "v4", "0", ["--density", "0.1"]), ("v1", "8", "v4", "1", [])]
 
 
 def sweep(extra):
