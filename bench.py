@@ -2,16 +2,22 @@
 """bench.py — headline benchmark of the HashNeRF hot path on B200 (contract: see DESIGN.md §Measurement).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload chair|scannet_t22|llff_acaq] [--scaling weak|strong] [--no-baselines] [--no-extras]
 
-ours       one "step" = one training iteration of BASELINE config 3 on every rank: 65536 rays/rank,
-           64+128 samples, 16 levels, T=2^19, finest 512 -> render fwd (coarse+fine), image+sparsity+TV
-           losses, backward, gradient all-reduce (N>1), RAdam.  `value` = rays/s with the ray batch already
-           in HBM; `e2e` = the same through the public API with pinned-host batches (H2D inside the timed
-           region, loss read back every step).  Also reported: the hash-encode kernel's achieved GB/s vs the
-           measured HBM peak (roofline), full-frame render Mpix/s (config 2), the oracle on the host cores
-           (cpu_baseline) and the reference's eager torch path on this GPU.
-reference  the reference's algorithm (oracle port: the Python reference cannot travel to the GPU box) on the
-           host cores, same metric/unit, bounded sample of the workload per step.
+ours       one "step" = one training iteration on every rank: render fwd (coarse + fine), image + sparsity + TV losses
+           (+ the depth / normal consumer loss of the ScanNet workload), backward, ONE gradient all-reduce (N > 1), RAdam.
+           Workloads (BASELINE.json configs):
+             chair        configs[2]  65536 rays/step, 64+128 samples, T=2^19, finest 512 (the headline, default)
+             scannet_t22  configs[3]  1296x968 indoor scene, T=2^22 (512 MiB tables, 512 MiB gradient all-reduce), normal
+                                      head on both networks, depth + normal maps consumed by a loss, near 0.1 / far 10
+             llff_acaq    configs[4]  1008x756 NDC rays, 64+64 samples, raw_noise_std 1, A-CAQ fake-quant fused into the
+                                      gather (learned per-level widths U(4,12), past warm-up) + quantised NeRFSmall
+           `value` = rays/s with the ray batch already in HBM; `e2e` = the same through Trainer.step with pinned-host
+           batches (H2D inside the timed region, loss read back every step).  `roofline` describes the dominant kernel
+           OF THE TIMED STEP (the fused backward of the fine pass), timed live with CUDA events on its stream.
+           weak scaling: 65536 rays per GPU; --scaling strong: 65536 rays in total.
+reference  the UNMODIFIED reference's training iteration (oracle/ref_train_step.py drives run_nerf.render ... RAdam.step
+           from oracle/_ref or /root/reference) on the host cores: 1024 rays per step, value = 1024 / median step time.
 """
 import argparse
 import json
@@ -28,17 +34,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MLP_MODE = os.environ.get("POCKETNERF_MLP", "bf16")     # "bf16": tcgen05 tensor-core NeRFSmall (north_star's 2e-3 mode); "fp32": FFMA
-RAYS_PER_RANK = 65536
-N_SAMPLES, N_IMPORTANCE = 64, 128
-HASH_BYTES_PER_POINT = 12 + 16 * 8 * 2 * 4 + 16 * 2 * 4      # 1164 B/point
+RAYS = 65536
+HASH_BYTES_PER_POINT = 12 + 16 * 8 * 2 * 4 + 16 * 2 * 4      # 1164 B/point (hash encode alone)
+# fused field kernels, algorithmic bytes per point: positions 12 + 16 levels x 8 corners x 8 B gathered or
+# scattered (counted once) + the saved bf16 feature tile 64 + raw / cotangent 16 + keep 1
+FIELD_BYTES_PER_POINT = 12 + 1024 + 64 + 16 + 1
+CPU_RAYS = 1024                                              # config-1 shape for the CPU baseline
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", 1400.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -102,7 +111,7 @@ class ClockSampler:
                 "window": window}
 
 
-def dist_setup(n):
+def dist_setup():
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
@@ -143,8 +152,30 @@ def time_steps(fn, steps, world):
     return max_over_ranks(e0.elapsed_time(e1), world)
 
 
-def cpu_reference_steps(steps, warmup, rays_per_step, threads):
-    """The oracle's train step on the host cores.  Returns (rays_per_s, ms_per_step)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference on the host cores / on this GPU (separate processes: the reference picks its device at import,
+# run_nerf.py:38, and set_default_tensor_type is process-global)
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_available():
+    from oracle import ref_shim
+    return ref_shim.available()
+
+
+def run_ref_subprocess(device, rays, steps, warmup, timeout_s):
+    env = dict(os.environ)
+    if device == "cpu":
+        env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, "-m", "oracle.ref_train_step", "--device", device, "--rays", str(rays), "--steps", str(steps),
+           "--warmup", str(warmup)]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout_s)
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("reference subprocess failed (rc %d): %s" % (r.returncode, r.stderr[-500:]))
+    return json.loads(lines[-1])
+
+
+def cpu_port_steps(steps, warmup, rays_per_step, threads):
+    """Fallback when no copy of the reference is present: the oracle port's train step on the host cores."""
     from indoor_nerf_b200 import synthetic
     from oracle.train_step import OracleModel, train_step
     torch.set_num_threads(threads)
@@ -153,65 +184,238 @@ def cpu_reference_steps(steps, warmup, rays_per_step, threads):
     batches = [synthetic.ray_batch(scene, rays_per_step, seed=100 + i) for i in range(2)]
     for i in range(warmup):
         train_step(model, *batches[i % 2])
-    t0 = time.perf_counter()
+    ts = []
     for i in range(steps):
+        t0 = time.perf_counter()
         train_step(model, *batches[i % 2])
-    dt = time.perf_counter() - t0
-    return rays_per_step * steps / dt, dt / steps * 1e3
+        ts.append(time.perf_counter() - t0)
+    med = float(np.median(ts))
+    return rays_per_step / med, med * 1e3
+
+
+def cpu_baseline(steps, warmup):
+    """(block for the JSON line).  ONE protocol for both places it is reported: 1024 rays per step (BASELINE config 1
+    shape), `warmup` untimed + `steps` timed iterations, rays/s from the MEDIAN step."""
+    threads = os.cpu_count() or 1
+    sample = ("%d rays/step of the chair workload (64+128 samples, T=2^19): one full train step (render fwd, img + sparsity + "
+              "TV losses, backward, RAdam), %d warm-up + %d timed, median" % (CPU_RAYS, warmup, steps))
+    if reference_available():
+        res = run_ref_subprocess("cpu", CPU_RAYS, steps, warmup, timeout_s=900)
+        where = os.path.relpath(res["reference_root"], ROOT) if res["reference_root"].startswith(ROOT) else res["reference_root"]
+        return {"value": res["rays_per_s"], "unit": "rays/s", "cores": res["threads"], "kind": "reference",
+                "ms_per_step": res["s_per_step_median"] * 1e3, "cpu_model": res.get("cpu_model"),
+                "sample": sample + "; the unmodified reference (%s) through oracle/ref_train_step.py" % where}
+    v, ms = cpu_port_steps(steps, warmup, CPU_RAYS, threads)
+    return {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "ms_per_step": ms,
+            "sample": sample + "; oracle port (no copy of the reference on this box)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    threads = os.cpu_count() or 1
-    total = args.steps + args.warmup
-    rays = 1024 if total <= 16 else (256 if total <= 64 else 64)
-    v, ms = cpu_reference_steps(args.steps, args.warmup, rays, threads)
-    line = {
-        "impl": "reference", "metric": "train_rays_per_s", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": "%d rays/step of the 65536-ray workload (64+128 samples, T=2^19), full train step "
-                                   "(render fwd, img+sparsity+TV losses, backward, RAdam) by the oracle on the host" % rays},
-        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    cb = cpu_baseline(max(1, args.steps), max(0, args.warmup))
+    return {
+        "impl": "reference", "metric": "train_rays_per_s", "value": cb["value"], "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, args.gpus, args.scaling),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    return line
 
 
-def workload_config(n):
-    return {"workload": "BASELINE configs[2]: chair-shaped synthetic Blender scene 400x400, HashNeRF training step, "
-                        "N_rand=65536 rays per GPU, 64 coarse + 128 importance samples, 16 levels, log2_hashmap 19, "
-                        "finest_res 512, NeRFSmall coarse+fine, white_bkgd, perturb=1",
-            "rays_per_gpu": RAYS_PER_RANK, "global_rays_per_step": RAYS_PER_RANK * n,
-            "points_per_ray": 2 * N_SAMPLES + N_IMPORTANCE, "parallelism": "dp%d" % n,
-            "l2_policy": "inputs larger than L2: 16.8 M points/step (201 MB positions, 2.1 GB features) stream "
-                         "through; the 64 MiB table set is L2-resident by design"}
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    "chair": dict(text="BASELINE configs[2]: chair-shaped synthetic Blender scene 400x400, HashNeRF training step, 64 coarse + "
+                       "128 importance samples, 16 levels, log2_hashmap 19, finest_res 512, NeRFSmall coarse+fine, white_bkgd, "
+                       "perturb=1", n_imp=128, log2T=19),
+    "scannet_t22": dict(text="BASELINE configs[3]: ScanNet-shaped indoor scene 1296x968 (room interior, 30 inward-looking views, "
+                             "near 0.1 / far 10), log2_hashmap 22 (512 MiB tables), normal head on both networks, depth + normal "
+                             "maps consumed by a structural-prior style loss, 64+128 samples", n_imp=128, log2T=22),
+    "llff_acaq": dict(text="BASELINE configs[4]: LLFF-shaped forward-facing scene 1008x756 in NDC (near 0 / far 1), 64+64 samples, "
+                           "raw_noise_std 1, A-CAQ quantised training: fake-quant fused into the hash gather with learned "
+                           "per-level widths U(4,12) past warm-up + quantised NeRFSmall first layer, log2_hashmap 19",
+                      n_imp=64, log2T=19),
+}
 
 
-def fp32_mode_leg(pn, step_resident):
+def rays_per_rank(world, scaling):
+    return RAYS if scaling == "weak" else RAYS // world
+
+
+def workload_config(name, n, scaling):
+    w = WORKLOADS[name]
+    rpr = rays_per_rank(n, scaling)
+    return {"workload": w["text"] + "; N_rand=%d rays per GPU" % rpr, "name": name,
+            "rays_per_gpu": rpr, "global_rays_per_step": rpr * n, "points_per_ray": 2 * 64 + w["n_imp"],
+            "parallelism": "dp%d" % n, "scaling": scaling,
+            "l2_policy": "inputs larger than L2: %.1f M points/step stream through; at log2_hashmap 19 the 64 MiB table set is "
+                         "L2-resident by design, at 22 (512 MiB) it is not" % (rpr * (128 + w["n_imp"]) / 1e6)}
+
+
+def structural_consumer_loss(scene, rays, dev):
+    """A torch loss that consumes depth_map and normal_map the way the reference's structural priors do
+    (run_nerf.py:1043-1148 -> structural_priors.combine_structural_losses_v2: depth prior, planarity, normal
+    consistency) — the callers of the path stay torch code; what matters here is that gradients flow back through
+    depth_map and normal_map into the normal head and the field."""
+    _, prior_depth, prior_normal = scene["prior_fn"](rays[0], rays[1])
+    prior_depth, prior_normal = prior_depth.to(dev), prior_normal.to(dev)
+
+    def fn(rgb, depth, extras):
+        ok = torch.isfinite(depth)
+        l_depth = (torch.where(ok, depth, prior_depth) - prior_depth).abs().mean()
+        n = extras["normal_map"]
+        l_normal = (1.0 - (n * prior_normal).sum(-1)).mean()
+        d2 = torch.where(ok, depth, prior_depth)
+        l_planar = (d2[2:] - 2 * d2[1:-1] + d2[:-2]).abs().mean()          # second differences over neighbouring batch rays
+        return 0.001 * l_depth + 0.0002 * l_normal + 0.001 * l_planar       # weights of configs/norcliffe_common_room.txt
+    return fn
+
+
+def build_workload(name, dev, rank, world, scaling, pn, pmodel, synthetic, Trainer, group):
+    """-> dict(trainer, pool (pinned host batches), pool_dev, set_batch(i), points_per_step, n_rays)."""
+    w = WORKLOADS[name]
+    n_rays = rays_per_rank(world, scaling)
+    if name == "chair":
+        scene = synthetic.blender_scene(400, 400, n_views=100)
+        a = pmodel.default_args(bounding_box=scene["bounding_box"], lrate=0.01)
+    elif name == "scannet_t22":
+        scene = synthetic.scannet_scene()
+        a = pmodel.default_args(bounding_box=scene["bounding_box"], lrate=0.01, log2_hashmap_size=22, predict_normals=True,
+                                white_bkgd=False, dataset_type="scannet")
+    else:
+        scene = synthetic.llff_scene()
+        a = pmodel.default_args(bounding_box=scene["bounding_box"], lrate=0.01, N_importance=64, raw_noise_std=1.0,
+                                white_bkgd=False, dataset_type="llff", use_quantization=True, quantization_bits=8)
+    torch.manual_seed(0)                                   # identical initial parameters on every rank
+    kw_train, kw_test, _, _, opt = pmodel.create_nerf(a, device=dev)
+    torch.manual_seed(1234 + rank)
+    tr = Trainer(a, kw_train, opt, scene["H"], scene["W"], scene["K"], scene["near"], scene["far"], group=group)
+    if name == "llff_acaq":
+        # A-CAQ past warm-up: table quantisers live (current_step >= warmup_steps), calibrated by the first step, learned
+        # soft bit-widths spread over 4..12 as the A-CAQ loop leaves them (run_nerf.py:1225-1252)
+        emb = kw_train["embed_fn"]
+        emb.current_step = emb.warmup_steps
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            for q in emb.quantizers:
+                q.soft_bits.fill_(float(4.0 + 8.0 * torch.rand((), generator=g)))
+    pool = [synthetic.ray_batch(scene, n_rays, seed=1000 * rank + i, pin=True) for i in range(4)]
+    pool_dev = [(r.to(dev), t.to(dev)) for r, t in pool]
+    extra = [structural_consumer_loss(scene, r, dev) for r, _ in pool] if name == "scannet_t22" else None
+
+    def set_batch(i):
+        if extra is not None:
+            tr.extra_loss_fn = extra[i % len(extra)]
+    return dict(trainer=tr, pool=pool, pool_dev=pool_dev, set_batch=set_batch, n_rays=n_rays, scene=scene, kw_train=kw_train,
+                kw_test=kw_test, points_per_step=n_rays * (128 + w["n_imp"]), args=a)
+
+
+def timed_workload(wl, steps, warmup, world, dev, clk=None, want_events=False):
+    """Warm-up through the e2e path, then `steps` resident + `steps` e2e iterations.  -> dict of timings."""
+    from indoor_nerf_b200 import _lib, ops
+    tr, pool, pool_dev = wl["trainer"], wl["pool"], wl["pool_dev"]
+    losses = []
+
+    def step_resident(i):
+        wl["set_batch"](i)
+        r, t = pool_dev[i % len(pool_dev)]
+        tr.step(r, t)
+
+    def step_e2e(i):
+        wl["set_batch"](i)
+        r, t = pool[i % len(pool)]
+        loss, _ = tr.step(r.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
+        losses.append(loss.item())
+
+    for i in range(warmup):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    if clk is not None:
+        clk.mark_start()
+    if want_events:
+        ops.KERNEL_EVENTS = []
+    l0 = _lib.launch_count()
+    ms = time_steps(step_resident, steps, world)
+    launches = _lib.launch_count() - l0
+    events, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
+    ms_e2e = time_steps(step_e2e, steps, world)
+    if clk is not None:
+        clk.mark_end()
+    h2d = pool[0][0].numel() * 4 + pool[0][1].numel() * 4
+    return dict(ms=ms, ms_e2e=ms_e2e, launches=launches, h2d=h2d, events=events or [], final_loss=losses[-1] if losses else None,
+                step_resident=step_resident)
+
+
+def kernel_event_summary(events):
+    """(name, n_points) -> mean ms over the launches recorded inside the timed region."""
+    acc = {}
+    for name, n, e0, e1 in events:
+        acc.setdefault((name, n), []).append(e0.elapsed_time(e1))
+    return {k: (float(np.mean(v)), len(v)) for k, v in acc.items()}
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of a kernel from the committed ncu capture of THIS round (profiles/r02_ncu_traffic.json,
+    written by scripts/ncu_summary.py from a `--set full` report) — a citation with its source, or None."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.isfile(p):
+        return None
     try:
-        pn.set_mlp_mode("fp32")
-        for i in range(2):
-            step_resident(i)
-        ms32 = time_steps(step_resident, 3, 1)
-        return {"value": RAYS_PER_RANK * 3 / (ms32 / 1e3), "unit": "rays/s", "ms_per_step": ms32 / 3,
-                "what": "same step with the fp32 FFMA NeRFSmall kernels and unfused hash kernels"}
-    except Exception as ex:
-        return {"error": repr(ex)}
-    finally:
-        pn.set_mlp_mode(MLP_MODE)
+        d = json.load(open(p))
+        e = d.get(kernel_key)
+        if e:
+            return {"bytes_per_launch": e["dram_bytes"], "points_per_launch": e.get("points"), "source": "profiles/r02_ncu_traffic.json",
+                    "report": e.get("report"), "kernel": e.get("kernel"), "captured": e.get("captured")}
+    except Exception:
+        pass
+    return None
 
 
-def hash_t22_leg(pn, ops, pts, dev, peak):
-    """BASELINE configs[3] table size (log2_hashmap 22: 512 MiB of tables, 4x the L2): the hash-encode kernels where the
-    table set cannot be L2-resident, same ray-ordered points."""
+def roofline_block(events, fine_points, hbm_peak, tf_peak, how):
+    ks = kernel_event_summary(events)
+    bwd = ks.get(("pn_field_bwd_bf16", fine_points))
+    fwd = ks.get(("pn_field_fwd_bf16", fine_points))
+    if bwd is None:
+        return None
+    t = bwd[0]
+    ach = FIELD_BYTES_PER_POINT * fine_points / (t * 1e-3) / 1e9
+    tr = ncu_traffic("field_bwd_fine")
+    blk = {"kernel": "field_bwd4_kernel (pn_field_bwd_bf16, fine pass: NeRFSmall backward on tcgen05 + hash-grid scatter)",
+           "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+           "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr,
+           "peak_source": how + " hbm_gbs (burst copy; the kernel is timed inside the training step)",
+           "algorithmic_bytes_per_point": FIELD_BYTES_PER_POINT, "points_per_launch": fine_points,
+           "ms_per_launch": t, "launches_timed": bwd[1],
+           "how": "CUDA events on the launching stream around every launch inside the timed region (ops.KERNEL_EVENTS)",
+           "tensor": {"achieved_tflops": 56064 * fine_points / (t * 1e-3) / 1e12, "peak_tflops": tf_peak,
+                      "frac": 56064 * fine_points / (t * 1e-3) / 1e12 / tf_peak},
+           "note": "algorithmic bytes: 1024 of the 1117 B/point are 8-byte scatter-adds into the 64 MiB gradient table, which the "
+                   "126 MB L2 absorbs, so DRAM traffic is far below this figure; what bounds the kernel is the SM's global-"
+                   "reduction port (~1 lane per clock) once the gradients are dense, and the MMA -> epilogue round latency "
+                   "before that (DESIGN.md section 4)"}
+    if fwd is not None:
+        tf_ = fwd[0]
+        blk["forward"] = {"kernel": "mlp_tc_fwd_kernel<3,SRC_HASH> (pn_field_fwd_bf16, fine pass)", "ms_per_launch": tf_,
+                          "achieved": FIELD_BYTES_PER_POINT * fine_points / (tf_ * 1e-3) / 1e9,
+                          "frac": FIELD_BYTES_PER_POINT * fine_points / (tf_ * 1e-3) / 1e9 / hbm_peak,
+                          "tensor_frac": 18688 * fine_points / (tf_ * 1e-3) / 1e12 / tf_peak}
+    blk["all_field_launches_ms"] = {"%s[%d pts]" % k: v[0] for k, v in ks.items()}
+    return blk
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# extra legs (rank 0, after the headline)
+# ---------------------------------------------------------------------------------------------------------------------
+def hash_kernel_leg(pn, ops, pts, dev, hbm_peak, log2T):
+    """The unfused hash-encode kernels (K1 / K1b, what HashEmbedder.forward launches) on the fine pass's point set."""
     try:
         box = (pts.min(0)[0].cpu() - 0.1, pts.max(0)[0].cpu() + 0.1)
-        emb = pn.HashEmbedder(box, log2_hashmap_size=22, finest_resolution=512).to(dev)
+        emb = pn.HashEmbedder(box, log2_hashmap_size=log2T, finest_resolution=512).to(dev)
         tables = [t.detach() for t in emb.tables()]
         P = pts.shape[0]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -226,7 +430,7 @@ def hash_t22_leg(pn, ops, pts, dev, peak):
             torch.cuda.synchronize()
             tf = e0.elapsed_time(e1) / 5
             dfeat = torch.randn(P, 32, device=dev)
-            flat = torch.zeros(16, 1 << 22, 2, device=dev)
+            flat = torch.zeros(16, 1 << log2T, 2, device=dev)
             ops.hash_encode_bwd(emb.grid(), list(flat.unbind(0)), pts, dfeat)
             torch.cuda.synchronize()
             e0.record()
@@ -236,20 +440,121 @@ def hash_t22_leg(pn, ops, pts, dev, peak):
             torch.cuda.synchronize()
             tb = e0.elapsed_time(e1) / 5
         ach = HASH_BYTES_PER_POINT * P / (tf * 1e-3) / 1e9
-        return {"kernel": "hash_fwd_kernel", "log2_hashmap_size": 22, "table_bytes": 16 * (1 << 22) * 8,
-                "points_per_launch": P, "ms_per_launch": tf, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "bound": "hbm",
-                "backward": {"kernel": "hash_bwd_kernel", "ms_per_launch": tb,
-                             "achieved": HASH_BYTES_PER_POINT * P / (tb * 1e-3) / 1e9},
-                "note": "algorithmic bytes (8 B per gathered corner); the table set is 4x the L2, so the fine levels "
-                        "miss it and every 8-byte gather moves a 32-byte DRAM sector"}
+        table_bytes = 16 * (1 << log2T) * 8
+        l2_resident = table_bytes < 100e6
+        tr = ncu_traffic("hash_fwd_t%d" % log2T)
+        return {"kernel": "hash_fwd_kernel", "log2_hashmap_size": log2T, "table_bytes": table_bytes,
+                "points_per_launch": P, "ms_per_launch": tf, "algorithmic_GBs": ach, "hbm_peak_GBs": hbm_peak,
+                "algorithmic_over_hbm_peak": ach / hbm_peak,
+                "bound": "l2 (table set resident in the 126 MB L2: NOT an HBM fraction)" if l2_resident else "hbm",
+                "dram_minimum_bytes_per_point": 12 + 128, "dram_minimum_GBs": (12 + 128) * P / (tf * 1e-3) / 1e9,
+                "traffic": tr,
+                "backward": {"kernel": "hash_bwd_kernel", "ms_per_launch": tb, "algorithmic_GBs": HASH_BYTES_PER_POINT * P / (tb * 1e-3) / 1e9,
+                             "algorithmic_over_hbm_peak": HASH_BYTES_PER_POINT * P / (tb * 1e-3) / 1e9 / hbm_peak,
+                             "cotangent": "dense random (worst case for the reduction port)"},
+                "note": "algorithmic bytes = 8 B per gathered corner; " + (
+                    "with the table set L2-resident the gathers never reach DRAM, so the ratio to the HBM peak can exceed 1 and is "
+                    "reported as algorithmic_over_hbm_peak, not as an HBM roofline fraction" if l2_resident else
+                    "the table set is 4x the L2: fine levels miss it and every 8-byte gather moves a 32-byte DRAM sector, coarse "
+                    "levels still hit")}
     except Exception as ex:
         return {"error": repr(ex)}
 
 
+def fused_kernel_leg(pn, ops, wl, dev, tf_peak):
+    try:
+        r, t = wl["pool_dev"][0]
+        n = r.shape[1]
+        P = n * 192
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z = torch.sort(2.0 + 4.0 * torch.rand(n, 192, device=dev), -1)[0]
+        pts3 = ops.make_points(r[0], r[1], z)
+        vd = r[1] / r[1].norm(dim=-1, keepdim=True)
+        net, embed = wl["kw_train"]["network_fine"], wl["kw_train"]["embed_fn"]
+        sh = pn.SHEncoder()
+        fw, bw = [], []
+        for it in range(6):
+            ops.KERNEL_EVENTS = []
+            out = pn.run_network(pts3, vd, net, embed, sh)
+            dout = torch.randn_like(out)
+            out.backward(dout)
+            torch.cuda.synchronize()
+            ev, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
+            for name, _, a, b in ev:
+                (fw if "fwd" in name else bw).append(a.elapsed_time(b))
+        tf, tb = float(np.median(fw[2:])), float(np.median(bw[2:]))
+        for prm in list(embed.parameters()) + list(net.parameters()):
+            prm.grad = None
+        return {"points_per_launch": P, "cotangent": "dense random",
+                "field_fwd": {"ms": tf, "algorithmic_GBs": FIELD_BYTES_PER_POINT * P / (tf * 1e-3) / 1e9,
+                              "tensor_TFLOPs": 18688 * P / (tf * 1e-3) / 1e12, "tensor_frac": 18688 * P / (tf * 1e-3) / 1e12 / tf_peak},
+                "field_bwd": {"ms": tb, "algorithmic_GBs": FIELD_BYTES_PER_POINT * P / (tb * 1e-3) / 1e9,
+                              "tensor_TFLOPs": 56064 * P / (tb * 1e-3) / 1e12, "tensor_frac": 56064 * P / (tb * 1e-3) / 1e12 / tf_peak},
+                "note": "kernel-only (CUDA events around the launch), random depths and a dense random cotangent"}
+    except Exception as ex:
+        ops.KERNEL_EVENTS = None
+        return {"error": repr(ex)}
+
+
+def fp32_mode_leg(pn, step_resident, n_rays):
+    try:
+        pn.set_mlp_mode("fp32")
+        for i in range(2):
+            step_resident(i)
+        ms32 = time_steps(step_resident, 3, 1)
+        return {"value": n_rays * 3 / (ms32 / 1e3), "unit": "rays/s", "ms_per_step": ms32 / 3,
+                "what": "same step with the fp32 FFMA NeRFSmall kernels and unfused hash kernels (1e-5 parity mode)"}
+    except Exception as ex:
+        return {"error": repr(ex)}
+    finally:
+        pn.set_mlp_mode(MLP_MODE)
+
+
+def render_leg(pn, pmodel, synthetic, dev):
+    scene2 = synthetic.blender_scene(800, 800, n_views=8)
+    a2 = pmodel.default_args(bounding_box=scene2["bounding_box"], finest_res=1024)
+    _, kw2, _, _, _ = pmodel.create_nerf(a2, device=dev)
+    c2w = torch.from_numpy(scene2["poses"][0][:3, :4])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def frame():
+        with torch.no_grad():
+            return pn.render(800, 800, scene2["K"], chunk=1 << 17, c2w=c2w, near=2., far=6., **kw2)
+    frame(); frame()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        frame()
+    e1.record()
+    torch.cuda.synchronize()
+    t_frame = e0.elapsed_time(e1) / 3
+    return {"workload": "BASELINE configs[1]: 800x800 test view, finest_res 1024, 64+128 samples",
+            "mpix_per_s": 0.64 / (t_frame * 1e-3), "ms_per_frame": t_frame}, scene2, kw2
+
+
+def render_sharded_leg(pn, pmodel, synthetic, dev, world, group):
+    """Pixel-sharded test-view rendering on all ranks (row blocks, no collective on the data path; one all-gather of the
+    finished frame): Mpix/s of whole frames, max over ranks."""
+    from indoor_nerf_b200 import parallel
+    scene2 = synthetic.blender_scene(800, 800, n_views=8)
+    a2 = pmodel.default_args(bounding_box=scene2["bounding_box"], finest_res=1024)
+    torch.manual_seed(0)
+    _, kw2, _, _, _ = pmodel.create_nerf(a2, device=dev)
+    c2w = torch.from_numpy(scene2["poses"][0][:3, :4])
+    ro, rd = pn.get_rays(800, 800, scene2["K"], c2w.to(dev))
+
+    def frame(i=0):
+        with torch.no_grad():
+            return parallel.render_sharded(lambda h, w, **k: pn.render(h, w, scene2["K"], chunk=1 << 17, **k), 800, 800, ro, rd,
+                                           group=group, gather=True, near=2., far=6., **kw2)
+    frame(); frame()
+    ms = time_steps(frame, 3, world) / 3
+    return {"workload": "configs[1] frame (800x800, finest 1024, 64+128), rows sharded over %d GPUs + all-gather" % world,
+            "mpix_per_s": 0.64 / (ms * 1e-3), "ms_per_frame": ms, "n_gpus": world}
+
+
 def io_legs(pn, scene, kw2, scene2, dev):
-    """on-GPU ray batching (rays/s of batch generation, bank bytes vs the reference's precomputed
-    tensor) and test-set evaluation through render_path (frames to pinned host memory + on-device PSNR)."""
+    """on-GPU ray batching and test-set evaluation through render_path."""
     out = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     try:
@@ -258,23 +563,22 @@ def io_legs(pn, scene, kw2, scene2, dev):
         bank = pn.RayBank(scene["H"], scene["W"], scene["K"], scene["poses"], images, list(range(n_img)), device=dev)
         bank.shuffle()
         for _ in range(3):
-            bank.next_batch(RAYS_PER_RANK)
+            bank.next_batch(RAYS)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(20):
-            bank.next_batch(RAYS_PER_RANK)
+            bank.next_batch(RAYS)
         e1.record()
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 20
-        out["ray_bank"] = {"rays_per_s": RAYS_PER_RANK / (t * 1e-3), "ms_per_batch": t, "batch": RAYS_PER_RANK,
-                           "bytes": bank.bytes_resident(),
+        out["ray_bank"] = {"rays_per_s": RAYS / (t * 1e-3), "ms_per_batch": t, "batch": RAYS, "bytes": bank.bytes_resident(),
                            "what": "use_batching batches generated from (image, pixel) ids, 100 views of 400x400"}
         del bank, images
     except Exception as ex:
         out["ray_bank"] = {"error": repr(ex)}
     try:
         poses = torch.from_numpy(scene2["poses"][:3])
-        gts = torch.rand(3, 800, 800, 3).pin_memory()          # ground truth as a loader would hold it: pinned host memory
+        gts = torch.rand(3, 800, 800, 3).pin_memory()
         kw = dict(kw2, near=2., far=6.)
         hwf = [800, 800, scene2["focal"]]
         pn.render_path(poses[:1], hwf, scene2["K"], 1 << 17, kw, gt_imgs=gts[:1])
@@ -283,18 +587,15 @@ def io_legs(pn, scene, kw2, scene2, dev):
         pn.render_path(poses, hwf, scene2["K"], 1 << 17, kw, gt_imgs=gts)
         dt = (time.perf_counter() - t0) / 3
         out["render_path"] = {"mpix_per_s": 0.64 / dt, "ms_per_frame": dt * 1e3, "d2h_bytes_per_frame": 800 * 800 * 16,
-                              "what": "render_path over 3 test views of configs[1] incl. host copies of rgb/depth and "
-                                      "on-device PSNR against host ground truth (wall clock, synchronised)"}
+                              "what": "render_path over 3 test views of configs[1] incl. host copies of rgb/depth and on-device "
+                                      "PSNR against pinned host ground truth (wall clock, synchronised)"}
     except Exception as ex:
         out["render_path"] = {"error": repr(ex)}
     return out
 
 
 def render_t22_leg(pn, pmodel, synthetic, dev):
-    """Test-view rendering at the ScanNet-config table size (log2_hashmap 22, 512 MiB of fp32 tables = 4x the L2) with a
-    quantised (A-CAQ, 8-bit) model: gathering fp32 entries, fake-quantising them in the gather (the reference's eval
-    semantics), and gathering u8 codes (HashEmbedder.pack_for_inference: 128 MiB; same embeddings bit for bit in the fp32 mode,
-    within fp32 rounding before the bf16 cast in this mode)."""
+    """Test-view rendering at log2_hashmap 22 with an 8-bit A-CAQ model: fp32 tables, fake-quant in the gather, u8 codes."""
     try:
         sc = synthetic.blender_scene(800, 800, n_views=2)
         a = pmodel.default_args(bounding_box=sc["bounding_box"], finest_res=1024, log2_hashmap_size=22,
@@ -338,209 +639,145 @@ def render_t22_leg(pn, pmodel, synthetic, dev):
         return {"error": repr(ex)}
 
 
+def short_workload_leg(name, dev, rank, world, scaling, mods, group, steps=6, warmup=3):
+    """A few steps of another BASELINE workload (all ranks take part): rays/s + the live kernel times."""
+    pn, pmodel, synthetic, Trainer = mods
+    try:
+        wl = build_workload(name, dev, rank, world, scaling, pn, pmodel, synthetic, Trainer, group)
+        res = timed_workload(wl, steps, warmup, world, dev, want_events=True)
+        n = wl["n_rays"]
+        ks = kernel_event_summary(res["events"])
+        out = {"config": workload_config(name, world, scaling), "value": n * world * steps / (res["ms"] / 1e3), "unit": "rays/s",
+               "ms_per_step": res["ms"] / steps, "steps": steps, "warmup": warmup,
+               "e2e": {"value": n * world * steps / (res["ms_e2e"] / 1e3), "unit": "rays/s", "h2d_bytes_per_step": res["h2d"],
+                       "d2h_bytes_per_step": 4},
+               "gpu_launches": int(res["launches"]), "final_loss": res["final_loss"],
+               "field_launches_ms": {"%s[%d pts]" % k: v[0] for k, v in ks.items()}}
+        emb = wl["kw_train"]["embed_fn"]
+        if name == "llff_acaq":
+            out["table_quantisers"] = {"calibrated": all(q.calibrated for q in emb.quantizers),
+                                       "soft_bits": [round(float(q.soft_bits), 2) for q in emb.quantizers]}
+        del wl
+        torch.cuda.empty_cache()
+        return out
+    except Exception as ex:
+        torch.cuda.empty_cache()
+        return {"error": repr(ex)}
+
+
 def run_ours(args):
     import indoor_nerf_b200 as pn
-    from indoor_nerf_b200 import _lib, model as pmodel, ops, synthetic
+    from indoor_nerf_b200 import model as pmodel, ops, synthetic
     from indoor_nerf_b200.trainer import Trainer
 
     pn.set_mlp_mode(MLP_MODE)
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_setup()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    torch.manual_seed(1234 + rank)
-    scene = synthetic.blender_scene(400, 400, n_views=100)
-    a = pmodel.default_args(bounding_box=scene["bounding_box"], lrate=0.01)
-    torch.manual_seed(0)                                   # identical initial parameters on every rank
-    kw_train, kw_test, _, _, opt = pmodel.create_nerf(a, device=dev)
-    torch.manual_seed(1234 + rank)
-    tr = Trainer(a, kw_train, opt, scene["H"], scene["W"], scene["K"], scene["near"], scene["far"],
-                 group=None if world == 1 else torch.distributed.group.WORLD)
-    pool = [synthetic.ray_batch(scene, RAYS_PER_RANK, seed=1000 * rank + i, pin=True) for i in range(4)]
-    pool_dev = [(r.to(dev), t.to(dev)) for r, t in pool]
-    h2d = pool[0][0].numel() * 4 + pool[0][1].numel() * 4
-
-    def step_resident(i):
-        r, t = pool_dev[i % len(pool_dev)]
-        tr.step(r, t)
-
-    losses = []
-
-    def step_e2e(i):
-        r, t = pool[i % len(pool)]
-        loss, _ = tr.step(r.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
-        losses.append(loss.item())
+    group = None if world == 1 else torch.distributed.group.WORLD
+    mods = (pn, pmodel, synthetic, Trainer)
+    wl = build_workload(args.workload, dev, rank, world, args.scaling, *mods, group)
+    n_rays = wl["n_rays"]
 
     with ClockSampler(local if rank == 0 else None) as clk:
-        for i in range(args.warmup):
-            step_e2e(i)
-        torch.cuda.synchronize()
-        clk.mark_start()
-        l0 = _lib.launch_count()
-        ms = time_steps(step_resident, args.steps, world)
-        launches = _lib.launch_count() - l0
-        ms_e2e = time_steps(step_e2e, args.steps, world)
-        clk.mark_end()
-    rays_total = RAYS_PER_RANK * world * args.steps
-    value = rays_total / (ms / 1e3)
-    e2e = rays_total / (ms_e2e / 1e3)
-
+        res = timed_workload(wl, args.steps, args.warmup, world, dev, clk=clk, want_events=True)
+    rays_total = n_rays * world * args.steps
+    hbm_peak, tf_peak, how = peaks()
     line = {
-        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "train_rays_per_s", "value": rays_total / (res["ms"] / 1e3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "bf16 NeRFSmall on tcgen05 (fp32 accumulate) + f32 hash grid / compositing / sampling" if MLP_MODE == "bf16"
-        else "f32", "data": "synthetic", "config": workload_config(world),
+        else "f32", "data": "synthetic", "config": workload_config(args.workload, world, args.scaling),
         "clocks": clk.summary(),
-        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
-        "final_loss": losses[-1] if losses else None,
+        "e2e": {"value": rays_total / (res["ms_e2e"] / 1e3), "unit": "rays/s", "h2d_bytes_per_step": res["h2d"],
+                "d2h_bytes_per_step": 4, "ms_per_step": res["ms_e2e"] / args.steps},
+        "gpu_launches": int(res["launches"]),
+        "final_loss": res["final_loss"],
     }
+    fine_points = n_rays * (64 + WORKLOADS[args.workload]["n_imp"])
+    if rank == 0 and MLP_MODE == "bf16":
+        line["roofline"] = roofline_block(res["events"], fine_points, hbm_peak, tf_peak, how)
 
-    if rank == 0:
-        # ---- roofline of the dominant kernel: hash-encode forward on the fine pass's point set ---------
-        embed = kw_train["embed_fn"]
-        P = RAYS_PER_RANK * (N_SAMPLES + N_IMPORTANCE)
-        r, t = pool_dev[0]
-        with torch.no_grad():
-            z = torch.sort(2.0 + 4.0 * torch.rand(RAYS_PER_RANK, N_SAMPLES + N_IMPORTANCE, device=dev), -1)[0]
-            pts = ops.make_points(r[0], r[1], z).reshape(-1, 3)
-            tables = [tt.detach() for tt in embed.tables()]
-            for _ in range(3):
-                ops.hash_encode_fwd(embed.grid(), tables, pts)
-            reps = 10
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                ops.hash_encode_fwd(embed.grid(), tables, pts)
-            e1.record()
-            torch.cuda.synchronize()
-            t_fwd = e0.elapsed_time(e1) / reps
-            dfeat = torch.randn(P, 32, device=dev)
-            flat = torch.zeros(16, 1 << 19, 2, device=dev)
-            for _ in range(2):
-                ops.hash_encode_bwd(embed.grid(), list(flat.unbind(0)), pts, dfeat)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                ops.hash_encode_bwd(embed.grid(), list(flat.unbind(0)), pts, dfeat)
-            e1.record()
-            torch.cuda.synchronize()
-            t_bwd = e0.elapsed_time(e1) / reps
-            del dfeat, flat, z
-        peak, how = peaks()
-        ach = HASH_BYTES_PER_POINT * P / (t_fwd * 1e-3) / 1e9
-        line["roofline"] = {"kernel": "hash_fwd_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": None, "peak_source": how,
-                            "algorithmic_bytes_per_point": HASH_BYTES_PER_POINT, "points_per_launch": P,
-                            "ms_per_launch": t_fwd,
-                            "backward": {"kernel": "hash_bwd_kernel", "ms_per_launch": t_bwd,
-                                         "achieved": HASH_BYTES_PER_POINT * P / (t_bwd * 1e-3) / 1e9}}
-        line["roofline"]["traffic"] = 1.890e9 if P == 12582912 else None   # ncu dram bytes read+write per launch (profiles/r01_ncu_full_hash_fwd_mlp_fwd_fp32.csv)
-        line["roofline_t22"] = hash_t22_leg(pn, ops, pts, dev, peak)
-        del pts
-        torch.cuda.empty_cache()
-        # ---- the fused field kernels of the bf16 mode (what the training step actually launches) ---------
-        if MLP_MODE == "bf16":
-            try:
-                r, t = pool_dev[0]
-                z = torch.sort(2.0 + 4.0 * torch.rand(RAYS_PER_RANK, N_SAMPLES + N_IMPORTANCE, device=dev), -1)[0]
-                pts3 = ops.make_points(r[0], r[1], z)
-                vd = r[1] / r[1].norm(dim=-1, keepdim=True)
-                net = kw_train["network_fine"]
-                sh = pn.SHEncoder()
-                fw, bw = [], []
-                for it in range(6):
-                    torch.cuda.synchronize()
-                    e0.record()
-                    out = pn.run_network(pts3, vd, net, embed, sh)
-                    e1.record()
-                    torch.cuda.synchronize()
-                    fw.append(e0.elapsed_time(e1))
-                    dout = torch.randn_like(out)
-                    torch.cuda.synchronize()
-                    e0.record()
-                    out.backward(dout)
-                    e1.record()
-                    torch.cuda.synchronize()
-                    bw.append(e0.elapsed_time(e1))
-                tf, tb = float(np.median(fw[2:])), float(np.median(bw[2:]))
-                tf_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0) \
-                    if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
-                line["fused_kernels"] = {
-                    "points_per_launch": P,
-                    "field_fwd": {"kernel": "mlp_tc_fwd_kernel<3,SRC_HASH>", "ms": tf,
-                                  "hbm_algorithmic_GBs": (12 + 1024 + 16 + 64 + 1) * P / (tf * 1e-3) / 1e9,
-                                  "tensor_TFLOPs": 18688 * P / (tf * 1e-3) / 1e12, "tensor_frac": 18688 * P / (tf * 1e-3) / 1e12 / tf_peak},
-                    "field_bwd": {"kernel": "mlp_tc_bwd_kernel<SRC_TILE> (+ torch memset/adds of the autograd node)", "ms": tb,
-                                  "hbm_algorithmic_GBs": (12 + 64 + 16 + 1 + 1024) * P / (tb * 1e-3) / 1e9,
-                                  "tensor_TFLOPs": 56064 * P / (tb * 1e-3) / 1e12, "tensor_frac": 56064 * P / (tb * 1e-3) / 1e12 / tf_peak},
-                    "note": "latency/L2-atomic bound, not HBM or tensor bound: see DESIGN.md §4 and profiles/"}
-                del pts3, z, out, dout
-                for prm in list(embed.parameters()) + list(net.parameters()):
-                    prm.grad = None
-            except Exception as ex:
-                line["fused_kernels"] = {"error": repr(ex)}
-            # the same training step in the fp32 (FFMA, 1e-5 parity) mode.  Single-GPU runs only: Trainer.step
-            # all-reduces, and this block runs on rank 0 alone.
-            if world == 1:
-                line["fp32_mode"] = fp32_mode_leg(pn, step_resident)
-        # ---- config 2: full 800x800 test-view render, finest_res 1024 -----------------------------------
+    extras = not args.no_extras
+    # ---- legs every rank takes part in --------------------------------------------------------------------------------
+    if extras and world > 1 and args.workload == "chair":
+        other = "strong" if args.scaling == "weak" else "weak"
         try:
-            scene2 = synthetic.blender_scene(800, 800, n_views=8)
-            a2 = pmodel.default_args(bounding_box=scene2["bounding_box"], finest_res=1024)
-            _, kw2, _, _, _ = pmodel.create_nerf(a2, device=dev)
-            c2w = torch.from_numpy(scene2["poses"][0][:3, :4])
-            def frame():
-                with torch.no_grad():
-                    return pn.render(800, 800, scene2["K"], chunk=1 << 17, c2w=c2w, near=2., far=6., **kw2)
-            frame(); frame()
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(3):
-                frame()
-            e1.record()
-            torch.cuda.synchronize()
-            t_frame = e0.elapsed_time(e1) / 3
-            line["render"] = {"workload": "BASELINE configs[1]: 800x800 test view, finest_res 1024, 64+128 samples",
-                              "mpix_per_s": 0.64 / (t_frame * 1e-3), "ms_per_frame": t_frame}
-            line.update(io_legs(pn, scene, kw2, scene2, dev))
+            wl2 = build_workload("chair", dev, rank, world, other, *mods, group)
+            r2 = timed_workload(wl2, 6, 3, world, dev)
+            if rank == 0:
+                line[other + "_scaling"] = {"value": wl2["n_rays"] * world * 6 / (r2["ms"] / 1e3), "unit": "rays/s",
+                                            "ms_per_step": r2["ms"] / 6, "rays_per_gpu": wl2["n_rays"],
+                                            "global_rays_per_step": wl2["n_rays"] * world, "steps": 6, "warmup": 3}
+            del wl2
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            if rank == 0:
+                line[other + "_scaling"] = {"error": repr(ex)}
+        try:
+            rs = render_sharded_leg(pn, pmodel, synthetic, dev, world, group)
+            if rank == 0:
+                line["render_sharded"] = rs
+        except Exception as ex:
+            if rank == 0:
+                line["render_sharded"] = {"error": repr(ex)}
+        torch.cuda.empty_cache()
+    if extras and args.workload == "chair":
+        wls = {}
+        for name in ("scannet_t22", "llff_acaq"):
+            r = short_workload_leg(name, dev, rank, world, args.scaling, mods, group)
+            if rank == 0:
+                wls[name] = r
+        if rank == 0:
+            line["workloads"] = wls
+
+    # ---- rank-0 legs ---------------------------------------------------------------------------------------------------
+    if rank == 0 and extras and args.workload == "chair":
+        r, t = wl["pool_dev"][0]
+        with torch.no_grad():
+            z = torch.sort(2.0 + 4.0 * torch.rand(n_rays, 192, device=dev), -1)[0]
+            pts = ops.make_points(r[0], r[1], z).reshape(-1, 3)
+        line["hash_kernels_t19"] = hash_kernel_leg(pn, ops, pts, dev, hbm_peak, 19)
+        line["hash_kernels_t22"] = hash_kernel_leg(pn, ops, pts, dev, hbm_peak, 22)
+        del pts, z
+        torch.cuda.empty_cache()
+        if MLP_MODE == "bf16":
+            line["fused_kernels"] = fused_kernel_leg(pn, ops, wl, dev, tf_peak)
+            if world == 1:            # Trainer.step all-reduces with a group, and this block runs on rank 0 alone
+                line["fp32_mode"] = fp32_mode_leg(pn, res["step_resident"], n_rays)
+        try:
+            line["render"], scene2, kw2 = render_leg(pn, pmodel, synthetic, dev)
+            line.update(io_legs(pn, wl["scene"], kw2, scene2, dev))
             del kw2
             torch.cuda.empty_cache()
             line["render_t22_quantised"] = render_t22_leg(pn, pmodel, synthetic, dev)
-        except Exception as ex:                                     # keep the headline even if this leg fails
+        except Exception as ex:
             line["render"] = {"error": repr(ex)}
         torch.cuda.empty_cache()
-        if world == 1 and not args.no_baselines:
-            # ---- reference eager path on this GPU (the oracle's ATen ops), for the >=50x target ------------
-            try:
-                from oracle.train_step import OracleModel, train_step
-                om = OracleModel(*scene["bounding_box"], log2T=19, finest=512, device=dev, lr=0.01)
-                r, t = pool_dev[0]
-                train_step(om, r, t)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(2):
-                    train_step(om, r, t)
-                torch.cuda.synchronize()
-                dt = (time.perf_counter() - t0) / 2
-                line["reference_eager_b200"] = {"value": RAYS_PER_RANK / dt, "unit": "rays/s", "ms_per_step": dt * 1e3,
-                                                "what": "oracle (the reference's eager ATen op sequence) on the same "
-                                                        "B200, same 65536-ray step, chunk 32768"}
-                del om
-                torch.cuda.empty_cache()
-            except Exception as ex:
-                line["reference_eager_b200"] = {"error": repr(ex)}
-            # ---- oracle on the host cores -----------------------------------------------------------------------
-            threads = os.cpu_count() or 1
-            v, msc = cpu_reference_steps(3, 1, 1024, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "ms_per_step": msc,
-                                    "sample": "1024 rays/step of the same workload (64+128 samples, T=2^19), full "
-                                              "train step by the oracle, 1 warm-up + 3 timed steps"}
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+    if rank == 0 and world == 1 and not args.no_baselines and args.workload == "chair":
+        # ---- the reference's own eager path on this GPU (denominator of the >= 50x target) and on the host cores ------
+        del wl
+        torch.cuda.empty_cache()
+        try:
+            if not reference_available():
+                raise RuntimeError("no copy of the reference on this box (oracle/_ref missing)")
+            r = run_ref_subprocess("cuda", RAYS, 2, 1, timeout_s=900)
+            line["reference_eager_b200"] = {"value": r["rays_per_s"], "unit": "rays/s", "ms_per_step": r["s_per_step_median"] * 1e3,
+                                            "kind": "reference",
+                                            "what": "the UNMODIFIED reference (run_nerf.render ... RAdam.step through oracle/ref_shim, "
+                                                    "torch.set_default_tensor_type cuda as run_nerf.py:1486) on the same B200, same "
+                                                    "65536-ray chair step, chunk 32768; 1 warm-up + median of 2"}
+            line["speedup_vs_reference_eager_b200"] = line["value"] / r["rays_per_s"]
+        except Exception as ex:
+            line["reference_eager_b200"] = {"error": repr(ex)[:400]}
+        try:
+            line["cpu_baseline"] = cpu_baseline(5, 1)
+        except Exception as ex:
+            line["cpu_baseline"] = {"error": repr(ex)[:400]}
     return line if rank == 0 else None
 
 
@@ -571,10 +808,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-baselines", action="store_true", help="skip the CPU / eager-GPU baseline legs")
+    ap.add_argument("--workload", default="chair", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-baselines", action="store_true", help="skip the reference legs (CPU / eager GPU)")
+    ap.add_argument("--no-extras", action="store_true", help="headline + roofline only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    with StdoutToStderr() as guard:
+    with StdoutToStderr():
         line = run_reference(args) if args.impl == "reference" else run_ours(args)
     if line is not None:
         emit(line)

@@ -73,6 +73,14 @@ def create_nerf(args, device="cuda"):
             model_fine.load_state_dict(ckpt["network_fine_state_dict"])
         embed_fn.load_state_dict(ckpt["embed_fn_state_dict"])
 
+    if torch.device(device).type == "cuda":
+        # one flat gradient buffer for the tables and both networks (ops.GradArena): the fused backward accumulates
+        # into it, a data-parallel step all-reduces it in one call
+        from . import ops
+        mlp_leaves = [p for net in (model, model_fine) if net is not None for k, p in net.named_parameters()
+                      if "quantizer" not in k]
+        embed_fn.grad_arena = ops.GradArena(embed_fn.tables(), mlp_leaves)
+
     render_kwargs_train = {
         "network_query_fn": network_query_fn, "perturb": args.perturb, "N_importance": args.N_importance,
         "network_fine": model_fine, "N_samples": args.N_samples, "network_fn": model, "embed_fn": embed_fn,

@@ -140,6 +140,9 @@ _FLAT_GRADS = {}
 
 def table_grad_buffer(tables):
     """The flat gradient buffer of `tables` with every level's view installed as .grad (zeroed / seeded as needed)."""
+    arena = arena_of(list(tables))
+    if arena is not None and len(tables) == len(arena.tables) and all(a is b for a, b in zip(tables, arena.tables)):
+        return arena.ensure().table_flat
     t0 = tables[0]
     L = len(tables)
     key = (t0.data_ptr(), L, tuple(t0.shape), str(t0.device))
@@ -166,6 +169,83 @@ def table_grad_buffer(tables):
         for l, t in enumerate(tables):
             t.grad = flat[l]
     return flat
+
+
+class GradArena:
+    """ONE flat fp32 gradient buffer for a whole model: [ table gradients L*T*2 | MLP gradients of every network ].
+
+    Every registered parameter's ``.grad`` is a view of it; the backward kernels accumulate into those views with
+    atomics and the autograd nodes return None for them (the "main grad" pattern of the table buffer above, extended
+    to the NeRFSmall weights).  A data-parallel step therefore all-reduces exactly one buffer with no packing or
+    copy-back, and ``optimizer.zero_grad()`` (set_to_none) is honoured: a parameter found without ``.grad`` gets its
+    segment zeroed before the next accumulation — with one memset when the whole model was released.
+    ``create_nerf`` builds the arena; parameters that are not registered (or whose storage moved since, e.g. after
+    ``.to()``) keep the ordinary autograd path.  Parameters are identified by their data pointer."""
+
+    def __init__(self, tables, mlp_params):
+        self.tables = list(tables)
+        self.mlp = list(mlp_params)
+        t0 = self.tables[0]
+        if not all(t.shape == t0.shape and t.dtype == torch.float32 and t.device == t0.device for t in self.tables):
+            raise _lib.PocketNerfError("GradArena: tables must share shape, dtype and device")
+        self.device = t0.device
+        off, self.views = 0, {}
+        segs = []
+        for p in self.tables + self.mlp:
+            segs.append((p, off))
+            off += (p.numel() + 3) // 4 * 4                          # 16-byte aligned segments
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        for p, o in segs:
+            self.views[p.data_ptr()] = self.flat[o:o + p.numel()].view(p.shape)
+            p._pn_arena = self
+        self.table_flat = self.flat[:len(self.tables) * t0.numel()].view((len(self.tables),) + tuple(t0.shape))
+
+    def params(self):
+        return self.tables + self.mlp
+
+    def covers(self, p):
+        v = self.views.get(p.data_ptr())
+        return v is not None and v.shape == p.shape and p.device == self.device and p.dtype == torch.float32
+
+    def view(self, p):
+        return self.views[p.data_ptr()]
+
+    def installed(self, p):
+        g = p.grad
+        return g is not None and g.data_ptr() == self.views[p.data_ptr()].data_ptr()
+
+    def valid(self):
+        return all(self.covers(p) for p in self.params())
+
+    def ensure(self):
+        """Install every view as its parameter's .grad; zero the segments of released parameters, fold in gradients that
+        another producer delivered to a fresh tensor.  Cheap when everything is already installed (one Python loop)."""
+        ps = self.params()
+        todo = [p for p in ps if not self.installed(p)]
+        if not todo:
+            return self
+        if len(todo) == len(ps) and all(p.grad is None for p in ps):
+            self.flat.zero_()
+        else:
+            for p in todo:
+                if p.grad is None:
+                    self.view(p).zero_()
+                else:
+                    self.view(p).copy_(p.grad)
+        for p in todo:
+            p.grad = self.view(p)
+        return self
+
+
+def arena_of(params):
+    """The GradArena that all of `params` are registered with and that still matches their storage, or None."""
+    a = getattr(params[0], "_pn_arena", None)
+    if a is None or not a.valid():
+        return None
+    if any(getattr(p, "_pn_arena", None) is not a or not a.covers(p) for p in params):
+        return None
+    return a
 
 
 class HashEncodeFn(torch.autograd.Function):
@@ -337,6 +417,33 @@ class MlpFn(torch.autograd.Function):
 
 
 _BWD_WORKSPACE = {}
+_FROZEN_SINK = {}
+# bench.py's live kernel timing: when a list is installed, the two fused field launches are bracketed by CUDA events
+# on the launching stream and (name, n_points, start, end) is appended; None (default) costs one `is None` test.
+KERNEL_EVENTS = None
+
+
+def _timed_call(name, n_points, *args):
+    if KERNEL_EVENTS is None:
+        return call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, *args)
+    e1.record()
+    KERNEL_EVENTS.append((name, int(n_points), e0, e1))
+
+
+def _frozen_table_sink(tables):
+    """Where the fused backward scatters when the tables do not require grad: one cached buffer per (shape, device),
+    never read (was: a fresh 64-512 MiB zero tensor per backward)."""
+    key = (len(tables), tuple(tables[0].shape), str(tables[0].device))
+    buf = _FROZEN_SINK.get(key)
+    if buf is None:
+        _FROZEN_SINK.clear()
+        buf = torch.zeros((len(tables),) + tuple(tables[0].shape), dtype=torch.float32, device=tables[0].device)
+        _FROZEN_SINK[key] = buf
+    return buf
+
 
 
 def _field_bwd_workspace(device):
@@ -373,12 +480,12 @@ class FieldFn(torch.autograd.Function):
             C = 7 if w.get("n0w") is not None else 4
             out = torch.empty((P, C), dtype=torch.float32, device=pts.device)
             keep = torch.empty((P,), dtype=torch.bool, device=pts.device)
-            need_bwd = any(t.requires_grad for t in params)
+            need_bwd = any(ctx.needs_input_grad[8:])     # all False under no_grad (render / eval): no feature tiles
             feat = torch.empty(((P + 127) // 128) * 8192, dtype=torch.uint8, device=pts.device) if need_bwd else None
             _check_tables(grid, tables)
             with _guard(pts):
                 ws = _weights_struct(w)
-                call("pn_field_fwd_bf16", ctypes.byref(grid), _ptr_array([t.detach() for t in tables]),
+                _timed_call("pn_field_fwd_bf16", P, ctypes.byref(grid), _ptr_array([t.detach() for t in tables]),
                      dptr(qparams, allow_none=True), ctypes.byref(ws), dptr(pts), dptr(dirs), int(S),
                      dptr(act_q, allow_none=True), P, dptr(out), dptr(keep, torch.bool),
                      dptr(feat, torch.uint8, allow_none=True), stream())
@@ -402,16 +509,27 @@ class FieldFn(torch.autograd.Function):
             if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):
                 flat = table_grad_buffer(tables)
             else:                               # frozen tables: the kernel still needs somewhere to scatter
-                flat = torch.zeros((ctx.n_tables,) + tuple(tables[0].shape), dtype=torch.float32, device=pts.device)
-            dw = {k: torch.zeros_like(w[k]) for k in _MLP_KEYS if w.get(k) is not None}
+                flat = _frozen_table_sink(tables)
+            # weight gradients: straight into the model's gradient arena where the weight is a registered leaf
+            # parameter (the kernel accumulates with atomics); through autograd otherwise (e.g. the fake-quantised W0)
+            arena = arena_of(list(tables))
+            dw, direct = {}, set()
+            for k, t in zip(ctx.keys, weights):
+                if (arena is not None and t.is_leaf and t.requires_grad and t.is_contiguous()
+                        and getattr(t, "_pn_arena", None) is arena and arena.covers(t)):
+                    arena.ensure()
+                    dw[k] = arena.view(t)
+                    direct.add(k)
+                else:
+                    dw[k] = torch.zeros_like(w[k])
             with _guard(pts):
                 ws, gs = _weights_struct(w), _weights_struct(dw)
                 wsp = _field_bwd_workspace(pts.device)
-                call("pn_field_bwd_bf16", ctypes.byref(ctx.grid), _ptr_array(list(flat.unbind(0))), ctypes.byref(ws),
+                _timed_call("pn_field_bwd_bf16", pts.shape[0], ctypes.byref(ctx.grid), _ptr_array(list(flat.unbind(0))), ctypes.byref(ws),
                      dptr(feat, torch.uint8), dptr(pts), dptr(dirs), int(ctx.S), dptr(ctx.act_q, allow_none=True),
                      dptr(keep, torch.bool), dptr(dout), pts.shape[0], ctypes.byref(gs), dptr(wsp, torch.uint8),
                      wsp.numel(), stream())
-            return (None,) * (8 + ctx.n_tables) + tuple(dw[k] for k in ctx.keys)
+            return (None,) * (8 + ctx.n_tables) + tuple(None if k in direct else dw[k] for k in ctx.keys)
         dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep, mode=ctx.mode)
         if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):
             flat = table_grad_buffer(tables)

@@ -45,13 +45,26 @@ def flat_table_grad(embed_fn):
     return flat
 
 
-def allreduce_gradients(embed_fn, nets, group=None):
-    """SUM all-reduce of every gradient the step produced: one call for the tables, one for everything else."""
-    flat = flat_table_grad(embed_fn)
-    if flat is not None:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    small = [p for m in nets for p in m.parameters() if p.grad is not None]
-    small += [p for n_, p in embed_fn.named_parameters() if not n_.startswith("embeddings.") and p.grad is not None]
+def allreduce_gradients(embed_fn, nets, group=None, async_op=False):
+    """SUM all-reduce of every gradient the step produced.  With the model's gradient arena (ops.GradArena, built by
+    create_nerf) that is ONE collective over one flat buffer — table gradients and the weights of both networks — with
+    no packing and no copy-back; gradients outside the arena (none in the stock configuration) go in a second, small
+    call.  Without an arena: one call for the flat table gradient, one for everything else.
+    Returns the list of work handles when async_op (the caller waits before the optimiser step)."""
+    works = []
+    arena = getattr(embed_fn, "grad_arena", None)
+    covered = set()
+    if arena is not None and arena.valid() and any(p.grad is not None for p in arena.params()):
+        arena.ensure()
+        works.append(dist.all_reduce(arena.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
+        covered = {id(p) for p in arena.params()}
+    else:
+        flat = flat_table_grad(embed_fn)
+        if flat is not None:
+            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
+        covered = {id(e.weight) for e in embed_fn.embeddings}
+    small = [p for m in nets for p in m.parameters() if p.grad is not None and id(p) not in covered]
+    small += [p for p in embed_fn.parameters() if p.grad is not None and id(p) not in covered]
     if small:
         buf = torch.cat([p.grad.reshape(-1) for p in small])
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
@@ -60,6 +73,7 @@ def allreduce_gradients(embed_fn, nets, group=None):
             k = p.grad.numel()
             p.grad.copy_(buf[off:off + k].view_as(p.grad))
             off += k
+    return [w for w in works if w is not None] if async_op else None
 
 
 def broadcast_parameters(modules, src=0, group=None):
@@ -77,11 +91,29 @@ def broadcast_parameters(modules, src=0, group=None):
 
 def sync_quantizer_calibration(quantizers, group=None):
     """Calibration statistics come from the local batch (quantization.py:97-119); make them the global
-    min / max so that every rank fake-quantises identically."""
-    for q in quantizers:
-        dist.all_reduce(q.running_min, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(q.running_max, op=dist.ReduceOp.MAX, group=group)
+    min / max so that every rank fake-quantises identically.  One MIN and one MAX collective for all quantisers."""
+    qs = [q for q in quantizers if q is not None]
+    if not qs:
+        return
+    lo = torch.stack([q.running_min.reshape(()) for q in qs])
+    hi = torch.stack([q.running_max.reshape(()) for q in qs])
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    for i, q in enumerate(qs):
+        q.running_min = lo[i].clone()
+        q.running_max = hi[i].clone()
         q.calibrate_minmax(q.running_min, q.running_max)
+
+
+def model_quantizers(embed_fn, nets):
+    """Every quantiser whose calibration depends on the batch: table levels, activation and weight quantisers."""
+    qs = list(embed_fn.quantizers) if getattr(embed_fn, "quantizers", None) is not None else []
+    for n in nets:
+        if getattr(n, "sigma_act_quantizers", None) is not None:
+            qs += list(n.sigma_act_quantizers)
+        if getattr(n, "sigma_weight_quantizer", None) is not None:
+            qs.append(n.sigma_weight_quantizer)
+    return qs
 
 
 def pixel_rows(H, rank_, world):

@@ -21,7 +21,13 @@ class RAdam(Optimizer):
         if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0):
             raise ValueError("Invalid betas: {}".format(betas))
         self.degenerated_to_sgd = degenerated_to_sgd
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # `buffer` is the reference's per-group memo of the rectification terms (radam.py:17-22, read at :60-78).  The
+        # update here recomputes them (two pow() per step), but the key is kept in every param group so that a
+        # checkpoint written by save_checkpoint loads into the reference's RAdam and vice versa.
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                      buffer=[[None, None, None] for _ in range(10)]))
+        for group in self.param_groups:
+            group["buffer"] = [[None, None, None] for _ in range(10)]
 
     @staticmethod
     def _rectification(step, beta1, beta2, degenerated_to_sgd):

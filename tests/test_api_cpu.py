@@ -284,7 +284,8 @@ def test_png_writer_roundtrip(tmp_path):
 
 
 def test_trainer_learning_rate_schedule():
-    """Trainer.decay_learning_rate follows run_nerf.py:1289-1293 (evaluated before global_step += 1 at :1475)."""
+    """Trainer.decay_learning_rate follows run_nerf.py:1289-1293: evaluated at the end of the iteration whose
+    global_step is g (before `global_step += 1`, :1475), it sets lrate * 0.1 ** (g / (lrate_decay * 1000))."""
     from types import SimpleNamespace
     from indoor_nerf_b200.trainer import Trainer
     p = torch.nn.Parameter(torch.zeros(3))
@@ -292,14 +293,39 @@ def test_trainer_learning_rate_schedule():
                        lr=0.01, betas=(0.9, 0.99))
     tr = Trainer.__new__(Trainer)
     tr.args, tr.opt, tr.step_idx = SimpleNamespace(lrate=0.01, lrate_decay=10), opt, 0
-    for step in (1, 500, 10000):
-        tr.step_idx = step
-        tr.decay_learning_rate()
-        want = 0.01 * (0.1 ** ((step - 1) / 10000))
-        assert all(g["lr"] == want for g in opt.param_groups)
+    for g in (0, 499, 9999):
+        tr.decay_learning_rate(g)
+        want = 0.01 * (0.1 ** (g / 10000))
+        assert all(grp["lr"] == want for grp in opt.param_groups)
     tr.args = SimpleNamespace(lrate=0.01)
-    tr.decay_learning_rate()                                      # no lrate_decay: left alone
+    tr.decay_learning_rate(5)                                     # no lrate_decay: left alone
     assert opt.param_groups[0]["lr"] == 0.01 * (0.1 ** (9999 / 10000))
+
+
+def test_trainer_resumes_schedule_from_checkpoint_step():
+    """A Trainer built with create_nerf's `start` (the checkpoint's global_step, run_nerf.py:299-307) continues the
+    schedule instead of restarting it: the learning rate is the reference's lrate * 0.1 ** (start / decay_steps) — what
+    the checkpointed optimiser state holds, since the reference saves after the update (:1289-1293 before :1345) — and
+    the TV term is cut for good after the first resumed iteration (`if i > 1000`, :1036-1037).  A Trainer without
+    `start` would reset lr to lrate * 0.1 ** 0 on its first step and re-enable TV for 1000 iterations."""
+    from types import SimpleNamespace
+    from indoor_nerf_b200.trainer import Trainer
+    params = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2))]
+    opt = pradam.RAdam([{"params": [params[0]], "weight_decay": 1e-6}, {"params": [params[1]], "eps": 1e-15}],
+                       lr=5e-4, betas=(0.9, 0.99))
+    args = SimpleNamespace(lrate=5e-4, lrate_decay=10, tv_loss_weight=1e-6, sparse_loss_weight=1e-10)
+    kw = {"embed_fn": SimpleNamespace(quantizers=None), "network_fn": SimpleNamespace(), "network_fine": None}
+    tr = Trainer(args, kw, opt, 4, 4, None, 2.0, 6.0, start=40000)
+    want = 5e-4 * (0.1 ** (40000 / 10000))                        # 5e-8, not 5e-4
+    assert tr.step_idx == 40000 and all(g["lr"] == want for g in opt.param_groups)
+    fresh = Trainer(args, kw, opt, 4, 4, None, 2.0, 6.0)
+    assert fresh.step_idx == 0 and all(g["lr"] == want for g in opt.param_groups)     # start=0 leaves the optimiser alone
+    # the counters after one (simulated) resumed step: lr(40000) again (the reference repeats global_step = start), TV off
+    tr.step_idx += 1
+    if tr.step_idx > 1000:
+        tr.tv_weight = 0.0
+    tr.decay_learning_rate(tr.step_idx - 1)
+    assert tr.tv_weight == 0.0 and all(g["lr"] == want for g in opt.param_groups)
 
 
 def test_no_cpu_path_for_the_io_ops():
