@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpocketnerf.so")
+# POCKETNERF_LIB selects another build of the same sources (tuning experiments: csrc/build.sh with PN_NVCC_EXTRA)
+LIB_PATH = os.environ.get("POCKETNERF_LIB") or os.path.join(_HERE, "csrc", "libpocketnerf.so")
 ABI_VERSION = 9
 MAX_LEVELS = 16
 QROW = 8

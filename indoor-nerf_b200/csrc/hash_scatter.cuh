@@ -18,9 +18,13 @@ struct GradPtrs {
 };
 
 // All 32 lanes must call this (lanes without a point pass g0 = g1 = 0 and any x).
+// direct_heads: warps with more run heads than this skip the reduction (default 20); max_len: runs are reduced in
+// sub-runs of at most this many lanes (power of two; default 32 = whole runs) — both tunable because the shuffle tree
+// and the reductions compete for the same LSU data pipe (scripts/sweep_scatter.py).
 template <bool EXACT_W = true>
 __device__ __forceinline__ void scatter_level(const HashGridDev &G, float2 *__restrict__ tab, int level,
-                                              const float xv[3], float g0, float g1, int lane) {
+                                              const float xv[3], float g0, float g1, int lane, int direct_heads = 20,
+                                              int max_len = 32) {
   const bool nz = (g0 != 0.f) || (g1 != 0.f);
   if (__ballot_sync(0xffffffffu, nz) == 0u) return;   // nothing to add anywhere in this warp
   Cell c;
@@ -28,9 +32,9 @@ __device__ __forceinline__ void scatter_level(const HashGridDev &G, float2 *__re
   // run heads: first lane, or voxel differs from the previous lane's
   const uint32_t px = __shfl_up_sync(0xffffffffu, c.hx0, 1), py = __shfl_up_sync(0xffffffffu, c.hy0, 1),
                  pz = __shfl_up_sync(0xffffffffu, c.hz0, 1);
-  const bool head = (lane == 0) || (px != c.hx0) || (py != c.hy0) || (pz != c.hz0);
+  const bool head = (lane == 0) || (px != c.hx0) || (py != c.hy0) || (pz != c.hz0) || ((lane & (max_len - 1)) == 0);
   const uint32_t heads = __ballot_sync(0xffffffffu, head);
-  if (__popc(heads) > 20) {                       // (almost) no sharing in this warp: direct atomics
+  if (__popc(heads) > direct_heads) {                       // (almost) no sharing in this warp: direct atomics
     if (nz) {
 #pragma unroll
       for (int k = 0; k < 8; ++k)
@@ -63,6 +67,63 @@ __device__ __forceinline__ void scatter_level(const HashGridDev &G, float2 *__re
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (a0[k] != 0.f || a1[k] != 0.f) atomicAdd(tab + corner_index(G, c, k), make_float2(a0[k], a1[k]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Serial run aggregation: ONE thread walks NS consecutive samples of a ray at one level, keeps the 8 x 2 corner sums of
+// the voxel it is in and flushes them (8 reductions) when the next sample leaves that voxel.  No shuffles: in the
+// warp-cooperative form above the shuffle tree is ~50 instructions per doubling step and its wavefronts share the LSU
+// data pipe with the reductions themselves (ncu, round 2: 82 % busy, 48 % of it shuffles, 2.3 G of the fused backward's
+// 3.1 G instructions in the scatter).  Runs that straddle two threads' segments are flushed twice — correct, and at the
+// coarse levels, where it happens, reductions are few anyway.  Samples with a zero gradient take part as zeros.
+// ------------------------------------------------------------------------------------------------------
+template <bool EXACT_W>
+__device__ __forceinline__ void scatter_segment(const HashGridDev &G, float2 *__restrict__ tab, int level,
+                                                const float *__restrict__ x, const float2 *g, int ns) {
+  // x: positions of the segment's first sample ([ns][3], read-only input), g: its gradients at this level ([ns] float2,
+  // written earlier in this kernel: plain loads).  The sample loop stays rolled: one sample's state live at a time.
+  float a0[8], a1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+  uint32_t phx = 0u, phy = 0u, phz = 0u;
+#pragma unroll 1
+  for (int s = 0; s < ns; ++s) {
+    const float xv[3] = {__ldg(x + 3 * s), __ldg(x + 3 * s + 1), __ldg(x + 3 * s + 2)};
+    const float2 gs = g[s];
+    Cell c;
+    point_cell<EXACT_W>(G, level, xv, c);
+    if (s > 0 && (c.hx0 != phx || c.hy0 != phy || c.hz0 != phz)) {
+      Cell pc;
+      pc.hx0 = phx; pc.hx1 = phx + 1u; pc.hy0 = phy; pc.hy1 = phy + PN_PRIME_Y; pc.hz0 = phz; pc.hz1 = phz + PN_PRIME_Z;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (a0[k] != 0.f || a1[k] != 0.f) atomicAdd(tab + corner_index(G, pc, k), make_float2(a0[k], a1[k]));
+        a0[k] = 0.f; a1[k] = 0.f;
+      }
+    }
+    phx = c.hx0; phy = c.hy0; phz = c.hz0;
+    const float fx1 = c.w[0], fx0 = EXACT_W ? pn_sub(1.0f, c.w[0]) : 1.0f - c.w[0];
+    const float fy1 = c.w[1], fy0 = EXACT_W ? pn_sub(1.0f, c.w[1]) : 1.0f - c.w[1];
+    const float fz1 = c.w[2], fz0 = EXACT_W ? pn_sub(1.0f, c.w[2]) : 1.0f - c.w[2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (EXACT_W) {
+        a0[k] = pn_add(a0[k], corner_weight_times(gs.x, c.w, k));
+        a1[k] = pn_add(a1[k], corner_weight_times(gs.y, c.w, k));
+      } else {
+        const float w = ((k & 4) ? fx1 : fx0) * ((k & 2) ? fy1 : fy0) * ((k & 1) ? fz1 : fz0);
+        a0[k] += gs.x * w;
+        a1[k] += gs.y * w;
+      }
+    }
+  }
+  if (ns > 0) {
+    Cell pc;
+    pc.hx0 = phx; pc.hx1 = phx + 1u; pc.hy0 = phy; pc.hy1 = phy + PN_PRIME_Y; pc.hz0 = phz; pc.hz1 = phz + PN_PRIME_Z;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (a0[k] != 0.f || a1[k] != 0.f) atomicAdd(tab + corner_index(G, pc, k), make_float2(a0[k], a1[k]));
   }
 }
 

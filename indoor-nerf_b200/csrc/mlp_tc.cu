@@ -135,6 +135,7 @@ struct FieldArgs {
   uint4 *featb;         // bf16 feature tiles, 8 KB per 128-point tile, tile layout (forward writes, backward reads)
   int scatter_split;    // backward: half 0 scatters levels [0, split), half 1 the rest
   int debug;            // PN_DEBUG_FLAGS (measurement only): 1 = skip the scatter work, 2 = skip the gather work
+  int sc_direct, sc_maxlen;   // scatter_level tuning (PN_SCATTER_DIRECT, PN_SCATTER_MAXLEN)
   long long *tlog;      // pn_debug_timeline buffer: [3 threads][tlog_cap] clock64 marks, or NULL
   int tlog_cap;
   PackedDev PK;         // SRC_PACKED: tables as integer codes (inference)
@@ -1423,18 +1424,24 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
 // round chain through a small ring in global memory (L2-resident: kRingSlots x 16 KB per CTA).
 //   warps 0-7   epilogue; after B5 each thread copies its half row of dX (TMEM, fp32) into the CTA's ring slot
 //   warp  8     MMA issuer (as v3)
-//   warps 9-15  scatter: 7 warps take (tile, quarter) items round-robin from the ring — any warp can take any quarter
-//               (the TMEM lane-quarter rule no longer applies), and they may lag the chain by kRingSlots tiles.
+//   warps 9-15  scatter: 7 warps take (tile, 4 levels) items round-robin from the ring — any warp can take any item
+//               (the TMEM lane-quarter rule no longer applies), and they may lag the chain by kRingSlots tiles; a lane
+//               walks 4 consecutive samples serially per level (scatter_segment: run aggregation without shuffles).
 // Why: with the training step's own gradients nearly every warp of 32 samples has some non-zero rows, so the scatter
 // costs its full ~230 instructions per level per warp; 4 scatter warps tied to the chain by a one-tile TMEM hand-off
 // (v3) took ~30 k cycles per tile against ~13 k for the chain.  What the scatter needs is issue slots from many warps
 // (the standalone scatter kernel reaches 71 % issue utilisation with 32 warps/SM), not a place in the chain.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kV4ScatterWarps = 7;
-constexpr int kV4Threads = kTcThreads + 32 + 32 * kV4ScatterWarps;      // 512
-constexpr int kV4EpiRegs = 80, kV4AuxRegs = 48;                         // 256*80 + 256*48 = 512*64 (launch bound at 2 CTAs/SM)
+#ifndef PN_V4_SCATTER_WARPS
+#define PN_V4_SCATTER_WARPS 3
+#endif
+constexpr int kV4ScatterWarps = PN_V4_SCATTER_WARPS;                    // 3 (12 warps per CTA) or 7 (16 warps)
+constexpr int kV4Threads = kTcThreads + 32 + 32 * kV4ScatterWarps;
+// register budget at 2 CTAs/SM (setmaxnreg per warpgroup): 12 warps -> launch bound 80: 256*88 + 128*64 = 384*80;
+//                                                           16 warps -> launch bound 64: 256*80 + 256*48 = 512*64
+constexpr int kV4EpiRegs = kV4ScatterWarps == 3 ? 88 : 80, kV4AuxRegs = kV4ScatterWarps == 3 ? 64 : 48;
 constexpr int kRingSlots = 4;
-static_assert(kV4Threads == 512, "register budget assumes 16 warps");
+static_assert(kV4ScatterWarps == 3 || kV4ScatterWarps == 7, "warps 8.. must fill whole warpgroups (setmaxnreg)");
 
 template <bool NORMALS>
 __global__ void __launch_bounds__(kV4Threads, 2)
@@ -1460,7 +1467,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   const int C = A.C;
 
   float *const cta_ring = ring + (size_t)blockIdx.x * (kRingSlots * kTcTile * 32);
-  if (warp >= 8) setmaxnreg_dec<kV4AuxRegs>();        // both warpgroups 8-11 and 12-15, one instruction
+  if (warp >= 8) setmaxnreg_dec<kV4AuxRegs>();        // warpgroup 8-11 (and 12-15), one instruction
   if (warp == 8) {
     // ---------------- MMA role ----------------
     const bool lead = elect_one();
@@ -1514,31 +1521,29 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   }
 
   if (warp >= 9) {
-    // ---------------- scatter role: kV4ScatterWarps warps, work item = (tile, quarter), taken round-robin ----------------
+    // ---------------- scatter role: kV4ScatterWarps warps; work item = (tile, 4 levels), taken round-robin -------------
+    // A lane owns 4 CONSECUTIVE samples of the tile (rows 4*lane .. +3) and walks them serially per level
+    // (scatter_segment): consecutive samples of a ray that share a voxel are summed in registers, no shuffles.
     const int sw = warp - 9;
     const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;      // tiles this CTA walks
     for (int64_t item = sw; item < my_tiles * 4; item += kV4ScatterWarps) {
       const int64_t n = item >> 2;
-      const int qd = (int)(item & 3), slot = (int)(n % kRingSlots);
-      const int64_t pt = (blockIdx.x + n * gridDim.x) * kTcTile + qd * 32 + lane;
-      const bool valid = pt < A.in.n_points;
-      float xv[3] = {0.f, 0.f, 0.f};
-      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
+      const int lq = (int)(item & 3), slot = (int)(n % kRingSlots);
+      const int64_t base = (blockIdx.x + n * gridDim.x) * kTcTile + 4 * lane;
+      const int64_t left = A.in.n_points - base;
+      const int ns = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
       mbar_wait(&ring_full[slot], (uint32_t)(n / kRingSlots) & 1);
-      // rows of this quarter with a gradient (published by the epilogue warps with the tile); 32 gradient-free samples
-      // (empty space, occluded samples) cost one shared-memory read
-      const uint32_t rows_nz = (ring_nz[slot][qd][0] | ring_nz[slot][qd][1]) & __ballot_sync(0xffffffffu, valid);
-      if (rows_nz != 0u && !(F.debug & 1)) {
-        const bool act = (rows_nz >> lane) & 1u;
-        // two values per level straight from the ring row (L2 / L1 hits), the next level's in flight during this one's
-        // scatter: no local-memory staging (the 107 KB x 2 of shared memory leave the SM almost no L1 for stack traffic)
-        const float2 *row = reinterpret_cast<const float2 *>(cta_ring + ((size_t)slot * kTcTile + qd * 32 + lane) * 32);
-        float2 gc = act ? row[0] : make_float2(0.f, 0.f);
+      // rows of this lane with a gradient (published by the epilogue warps with the tile; rows past n_points are zero)
+      const uint32_t mq = ring_nz[slot][lane >> 3][0] | ring_nz[slot][lane >> 3][1];
+      const uint32_t mine = (mq >> ((lane & 7) * 4)) & 0xFu;
+      if (mine != 0u && !(F.debug & 1)) {
+        // ring slot layout [level][row] float2: this lane's 4 rows of one level are 32 contiguous bytes
+        const float2 *lv = reinterpret_cast<const float2 *>(cta_ring + (size_t)slot * (kTcTile * 32)) + 4 * lane;
 #pragma unroll 1
-        for (int l = 0; l < F.G.n_levels; ++l) {
-          const float2 gn = (act && l + 1 < F.G.n_levels) ? row[l + 1] : make_float2(0.f, 0.f);
-          scatter_level<false>(F.G, F.D.t[l], l, xv, gc.x, gc.y, lane);
-          gc = gn;
+        for (int li = 0; li < 4; ++li) {
+          const int l = lq * 4 + li;
+          if (l >= F.G.n_levels) break;
+          scatter_segment<false>(F.G, F.D.t[l], l, F.pts + 3 * base, lv + (size_t)l * kTcTile, ns);
         }
       }
       __syncwarp();
@@ -1714,12 +1719,13 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       float v[16];
       tmem_ld16(lane_addr + TM_D1 + half * 16, v);
       tmem_ld_wait();
-      float4 *row = reinterpret_cast<float4 *>(cta_ring + ((size_t)slot * kTcTile + p) * 32 + half * 16);
+      // slot layout [level][row] float2 (a warp stores 256 contiguous bytes per level)
+      float2 *col = reinterpret_cast<float2 *>(cta_ring + (size_t)slot * (kTcTile * 32)) + (size_t)(half * 8) * kTcTile + p;
       bool nzr = false;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        nzr = nzr || v[4 * c] != 0.f || v[4 * c + 1] != 0.f || v[4 * c + 2] != 0.f || v[4 * c + 3] != 0.f;
+      for (int i = 0; i < 8; ++i) {
+        col[(size_t)i * kTcTile] = make_float2(v[2 * i], v[2 * i + 1]);
+        nzr = nzr || v[2 * i] != 0.f || v[2 * i + 1] != 0.f;
       }
       const uint32_t nzm = __ballot_sync(0xffffffffu, nzr && valid);
       fence_before_sync();                             // the tcgen05.ld above precedes the next tile's first MMA (via `ready`)
@@ -1954,6 +1960,15 @@ static int fill_field(FieldArgs &F, const pn_hash_grid *grid, const float *const
     dbg = e ? atoi(e) : 0;
   }
   F.debug = dbg;
+  static int sc_direct = -1, sc_maxlen = -1;
+  if (sc_direct < 0) {
+    const char *a = getenv("PN_SCATTER_DIRECT"), *b = getenv("PN_SCATTER_MAXLEN");
+    sc_direct = a ? atoi(a) : 20;
+    sc_maxlen = b ? atoi(b) : 32;
+    if (sc_maxlen != 1 && sc_maxlen != 2 && sc_maxlen != 4 && sc_maxlen != 8 && sc_maxlen != 16) sc_maxlen = 32;
+  }
+  F.sc_direct = sc_direct;
+  F.sc_maxlen = sc_maxlen;
   F.tlog = g_tlog_buf;
   F.tlog_cap = g_tlog_cap;
   return 0;

@@ -117,25 +117,29 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// One probe: the thread is suspended in hardware until the phase completes or a time limit passes.  The limit is given
+// explicitly (nanoseconds): with the default, the ~9 waits per tile of 17 warps re-probed so often that mbarrier traffic
+// was 70 % of the kernel's shared-memory wavefronts and the LSU data pipe sat at 82 % (ncu, round 2) — in a kernel
+// whose real work on that pipe is reductions and gathers.  Completion still wakes the thread at once.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar_addr), "r"(parity)
+      : "r"(bar_addr), "r"(parity), "r"(20000u)
       : "memory");
   return ok;
 }
 // Bounded spin: a protocol bug must surface as a launch failure (trap), never as a GPU that hangs until the
 // watchdog of whoever launched us fires.  try_wait suspends in hardware for up to its time limit per probe,
-// so 2^22 failed probes is at least tens of milliseconds — orders of magnitude beyond any legitimate wait in these kernels.
+// so 2^22 failed probes is at least tens of milliseconds (seconds with the 20 us limit below) — orders of magnitude beyond any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t spins = 0;
   while (!mbar_try_wait(a, parity)) {
-    if (++spins == (1u << 22)) __trap();
+    if (++spins == (1u << 20)) __trap();
   }
 }
 // one arrival of the executing thread (release semantics at CTA scope)
