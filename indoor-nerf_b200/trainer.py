@@ -49,14 +49,7 @@ class Trainer:
         """batch_rays [2,N,3], target_s [N,3] (this rank's shard).  Returns (loss, psnr) as 0-d device tensors."""
         rgb, depth, acc, extras = render(self.H, self.W, self.K, chunk=chunk or batch_rays.shape[1], rays=batch_rays,
                                          retraw=True, near=self.near, far=self.far, **self.kw)
-        if self.world > 1 and self._uncalibrated:
-            # Quantisers calibrate from the LOCAL shard during the forward above (quantization.py:97-119).  Which ones
-            # calibrate in a given step depends only on step counters, so every rank has the same `fresh` list: make
-            # their statistics the global min / max before any rank fake-quantises with them again.
-            fresh = [q for q in self._uncalibrated if q.calibrated]
-            if fresh:
-                parallel.sync_quantizer_calibration(fresh, self.group)
-                self._uncalibrated = [q for q in self._uncalibrated if not q.calibrated]
+        self._sync_fresh_quantizers()
         self.opt.zero_grad()
         loss, img_loss = self.losses(rgb, extras, target_s, depth)
         loss.backward()
@@ -68,6 +61,18 @@ class Trainer:
             self.tv_weight = 0.0
         self.decay_learning_rate(self.step_idx - 1)
         return loss.detach(), mse2psnr(img_loss.detach())
+
+    def _sync_fresh_quantizers(self):
+        """Quantisers calibrate from the LOCAL shard during the forward (quantization.py:97-119).  Which ones calibrate in
+        a given step depends only on step counters, so every rank has the same `fresh` list: make their statistics the
+        global min / max before any rank fake-quantises with them again (else the replicas diverge and the summed
+        gradient is no longer the single-process gradient)."""
+        if self.world <= 1 or not self._uncalibrated:
+            return
+        fresh = [q for q in self._uncalibrated if q.calibrated]
+        if fresh:
+            parallel.sync_quantizer_calibration(fresh, self.group)
+            self._uncalibrated = [q for q in self._uncalibrated if not q.calibrated]
 
     def decay_learning_rate(self, global_step):
         """run_nerf.py:1289-1293: lr = lrate * 0.1 ** (global_step / (lrate_decay * 1000)) on every group (a host scalar;

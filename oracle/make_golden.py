@@ -266,9 +266,19 @@ def main():
         query = lambda inputs, viewdirs, fn: RN.run_network(inputs, viewdirs, fn, embed_fn=emb, embeddirs_fn=sh)
         for p in list(emb.parameters()) + list(net0.parameters()) + list(net1.parameters()):
             p.requires_grad_(True); p.grad = None
+        # record the depths raw2outputs is called with (second call = the sort-merged fine depths), so that a test can
+        # feed the fine pass the reference's exact samples and hold it to the fp32 tolerance
+        z_seen = []
+        real_r2o = RN.raw2outputs
+
+        def spy_r2o(raw, z_vals, *a, **k):
+            z_seen.append(z_vals.detach().clone())
+            return real_r2o(raw, z_vals, *a, **k)
+        RN.raw2outputs = spy_r2o
         ret = RN.render_rays(rays, net0, query, 64, embed_fn=emb, retraw=True, perturb=perturb,
                              N_importance=S_imp, network_fine=net1, white_bkgd=white, raw_noise_std=std,
                              predict_normals=normals)
+        RN.raw2outputs = real_r2o
         RN.torch.rand, RN.torch.randn = real_rand, real_randn
         target = torch.from_numpy(rs.rand(N, 3).astype(np.float32))
         loss = ((ret["rgb_map"] - target) ** 2).mean() + ((ret["rgb0"] - target) ** 2).mean() \
@@ -287,6 +297,7 @@ def main():
         save("render_rays_" + tag, rays=rays, t_rand=t_rand, u=u, noise0=n0, noise1=n1, target=target,
              box_min=np.array(box[0], np.float32), box_max=np.array(box[1], np.float32), log2T=log2T,
              salt=21, amp=0.3, perturb=perturb, raw_noise_std=std, white=white, N_importance=S_imp, loss=loss,
+             z_coarse=z_seen[0], z_fine=z_seen[1],
              **{"w0_" + k: v for k, v in w0.items()}, **{"w1_" + k: v for k, v in w1.items()},
              **{k: ret[k] for k in keys}, **g)
 

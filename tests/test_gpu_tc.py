@@ -268,6 +268,12 @@ def test_fused_field_kernels_match_unfused(N):
         assert _rel(o1, o2)[0] < 2e-3, ("fused forward", _rel(o1, o2))        # features are bf16-rounded once in both
         for l in (0, 5, 10, 15):
             assert _rel(t1[l], t2[l])[0] < 2e-2, ("table grad level %d" % l, _rel(t1[l], t2[l]))
+        # The fused backward takes its voxel indices from point_cell<false> (reciprocal multiply + exact fallback), the
+        # unfused scatter from the reference form: the SETS of table rows that received a gradient must be identical at
+        # every level — the indices are bit-exact in the bf16 mode too
+        for l in range(16):
+            s1, s2 = (t1[l] != 0).any(-1), (t2[l] != 0).any(-1)
+            assert bool((s1 == s2).all()), ("gradient support differs at level %d: %d rows" % (l, int((s1 != s2).sum())))
         for a, b in zip(w1, w2):
             assert _rel(a, b)[0] < 2e-2, ("weight grad", _rel(a, b))
 
@@ -336,6 +342,22 @@ def test_render_bf16_mode_vs_fp32_mode():
     assert rep["stable_ray_fraction"] > 0.02
     for k in ["rgb_map", "acc_map", "depth_map"]:
         assert rep[k][0] < 2e-3 and rep[k][1] < 2e-3, (k, rep[k])
+    # ALL rays: whatever exceeds 2e-3 must be one of the enumerated sigma ~ 0 rays (`~stable`: some sample within 5 % of the
+    # median |sigma| of zero, or a sign flip between the modes), never a ray clear of the discontinuity; their number is
+    # bounded by the size of that set, and the worst of them stays a bounded error (an alpha flipping between 0 and 1 on
+    # one sample), not garbage
+    for k in ["rgb_map", "acc_map", "depth_map"]:
+        a, b = a16[k].detach(), a32[k].detach()
+        fin = torch.isfinite(b) & torch.isfinite(a)
+        err = ((a - b).abs() / b[fin].abs().max()).reshape(N, -1).amax(-1)
+        err = torch.where(torch.isfinite(err), err, torch.zeros_like(err))
+        over = err > 2e-3
+        assert not bool((over & stable).any()), (k, "a stable ray exceeds 2e-3")
+        assert int(over.sum()) <= int((~stable).sum()), (k, int(over.sum()), int((~stable).sum()))
+        assert rep[k][2] <= 1.0 + 1e-6, (k, "all-ray max", rep[k][2])
+    print("rays beyond 2e-3 (all within the %d sigma~0 rays):" % int((~stable).sum()),
+          {k: int((((a16[k] - a32[k]).abs() / a32[k][torch.isfinite(a32[k])].abs().max()).reshape(N, -1).amax(-1) > 2e-3).sum())
+           for k in ["rgb_map", "acc_map"]})
 
     # (B) the whole coarse + fine step: typical ray, loss, gradients
     (r32, t32, w32, l32), (r16, t16, w16, l16) = run("fp32", 128), run("bf16", 128)

@@ -61,6 +61,87 @@ def _allreduce(rank, world):
     return ok
 
 
+def _arena_allreduce(rank, world):
+    """With the model's gradient arena (ops.GradArena) the whole step's gradients — tables and both networks — go
+    through exactly ONE all_reduce call on one flat buffer; a parameter outside the arena gets the second, small call."""
+    from indoor_nerf_b200 import ops, parallel
+    emb, net = _models()
+    arena = ops.GradArena(emb.tables(), [p for p in net.parameters()])
+    emb.grad_arena = arena
+    assert arena.valid() and arena_ok(arena, emb, net)
+    arena.ensure()
+    assert all(p.grad is not None and p.grad.data_ptr() == arena.view(p).data_ptr() for p in arena.params())
+    arena.flat.fill_(float(rank + 1))
+    extra = torch.nn.Parameter(torch.zeros(5))
+    extra.grad = torch.full((5,), float(rank + 1))
+    calls = []
+    real = dist.all_reduce
+
+    def counting(t, *a, **k):
+        calls.append(t.numel())
+        return real(t, *a, **k)
+    dist.all_reduce = counting
+    try:
+        parallel.allreduce_gradients(emb, [net, torch.nn.ParameterList([extra])], dist.group.WORLD)
+    finally:
+        dist.all_reduce = real
+    ok = calls == [arena.numel, 5]
+    ok = ok and bool((arena.flat == 3.0).all()) and bool((extra.grad == 3.0).all())
+    ok = ok and all(bool((e.weight.grad == 3.0).all()) for e in emb.embeddings)
+    # zero_grad(set_to_none) is honoured: the next ensure() re-zeroes with the views re-installed
+    for p in arena.params():
+        p.grad = None
+    arena.ensure()
+    ok = ok and float(arena.flat.abs().sum()) == 0.0 and emb.embeddings[3].weight.grad.data_ptr() == arena.view(emb.embeddings[3].weight).data_ptr()
+    # a gradient delivered to a fresh tensor by another producer is folded in, not lost
+    net.sigma_net[0].weight.grad = torch.full_like(net.sigma_net[0].weight, 2.0)
+    arena.ensure()
+    ok = ok and bool((arena.view(net.sigma_net[0].weight) == 2.0).all())
+    return ok
+
+
+def arena_ok(arena, emb, net):
+    t0 = emb.embeddings[0].weight
+    return arena.table_flat.shape == (16,) + tuple(t0.shape) and arena.numel >= 16 * t0.numel() + sum(p.numel() for p in net.parameters())
+
+
+def _trainer_quantizer_sync(rank, world):
+    """Trainer._sync_fresh_quantizers: quantisers that calibrated from the LOCAL shard in this step's forward end the step
+    with identical (global min / max) state on every rank; nothing is exchanged once all are calibrated."""
+    import indoor_nerf_b200 as pn
+    from indoor_nerf_b200 import parallel
+    from indoor_nerf_b200.trainer import Trainer
+    torch.manual_seed(0)
+    emb = pn.HashEmbedder((torch.tensor([-1.0] * 3), torch.tensor([1.0] * 3)), log2_hashmap_size=6, use_quantization=True)
+    net = pn.NeRFSmall(num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, input_ch=32, input_ch_views=16,
+                       use_quantization=True)
+    tr = Trainer.__new__(Trainer)
+    tr.world, tr.group = world, dist.group.WORLD
+    qs = parallel.model_quantizers(emb, [net])
+    tr._uncalibrated = [q for q in qs if not q.calibrated]
+    n_all = len(tr._uncalibrated)
+    tr._sync_fresh_quantizers()                                   # nothing calibrated yet: no collective, list unchanged
+    ok = len(tr._uncalibrated) == n_all == 16 + 2
+    # "forward": the MLP quantisers calibrate on step 0, from rank-dependent statistics
+    net.sigma_act_quantizers[0].calibrate_minmax(torch.tensor(0.0), torch.tensor(1.0 + rank))
+    net.sigma_weight_quantizer.calibrate_minmax(torch.tensor(-0.5 - rank), torch.tensor(0.25))
+    tr._sync_fresh_quantizers()
+    ok = ok and len(tr._uncalibrated) == 16
+    ok = ok and float(net.sigma_act_quantizers[0].running_max) == 2.0 and float(net.sigma_act_quantizers[0].range_scale) == 2.0
+    ok = ok and float(net.sigma_weight_quantizer.running_min) == -1.5 and float(net.sigma_weight_quantizer.range_scale) == 3.0
+    # later: the 16 table quantisers calibrate together (current_step reaches warmup_steps on every rank at once)
+    for l, q in enumerate(emb.quantizers):
+        q.calibrate_minmax(torch.tensor(-1e-4 * (l + 1) * (rank + 1)), torch.tensor(1e-4 * (l + 2)))
+    tr._sync_fresh_quantizers()
+    ok = ok and tr._uncalibrated == []
+    state = torch.stack([torch.stack([q.running_min, q.running_max, q.range_scale.detach(), q.v_max.detach()]) for q in emb.quantizers])
+    other = [torch.zeros_like(state) for _ in range(world)]
+    dist.all_gather(other, state)
+    ok = ok and all(torch.equal(o, state) for o in other)
+    ok = ok and abs(float(emb.quantizers[3].running_min) + 8e-4) < 1e-9
+    return ok
+
+
 def _loss_scaling(rank, world):
     """Linear model stand-in for the renderer: gradient of the scaled per-rank losses, summed, must equal the
     gradient of the reference loss on the whole batch."""
@@ -181,6 +262,14 @@ def test_ray_bank_shards_and_permutation_sync():
 
 def test_allreduce_gradients():
     assert all(_run("_allreduce"))
+
+
+def test_gradient_arena_is_one_collective():
+    assert all(_run("_arena_allreduce"))
+
+
+def test_trainer_syncs_quantizer_calibration_across_ranks():
+    assert all(_run("_trainer_quantizer_sync"))
 
 
 def test_loss_scaling_sums_to_global_gradient():
