@@ -15,6 +15,14 @@ _MLP_KEYS = ("s0", "s1", "c0", "c1", "c2", "n0w", "n0b", "n2w", "n2b")
 _MLP_MODE = os.environ.get("POCKETNERF_MLP", "fp32")
 
 
+# diagnostic: run the bf16 mode through the UNFUSED kernels (exact fp32 hash kernels + tcgen05 MLP on fp32 feature rows)
+_BF16_UNFUSED = bool(os.environ.get("PN_BF16_UNFUSED"))
+# diagnostic (unfused path only): PN_EXP=fwd16_bwd32 / fwd32_bwd16 mixes the arithmetic of the two directions
+_EXP = os.environ.get("PN_EXP", "")
+_EXP_FWD = "bf16" if "fwd16" in _EXP else ("fp32" if "fwd32" in _EXP else None)
+_EXP_BWD = "bf16" if "bwd16" in _EXP else ("fp32" if "bwd32" in _EXP else None)
+
+
 def set_mlp_mode(mode):
     global _MLP_MODE
     if mode not in ("fp32", "bf16"):
@@ -473,7 +481,7 @@ class FieldFn(torch.autograd.Function):
         dirs = fcontig(viewdirs)
         w = {k: fcontig(t.detach()) for k, t in zip(keys, weights)}
         ctx.mode = _MLP_MODE
-        ctx.fused = ctx.mode == "bf16" and grid.n_levels == 16 and pts.shape[0] > 0
+        ctx.fused = ctx.mode == "bf16" and grid.n_levels == 16 and pts.shape[0] > 0 and not _BF16_UNFUSED
         if ctx.fused:
             # one kernel: hash encode -> SH -> NeRFSmall (tcgen05) -> keep mask; features saved as bf16 operand tiles
             P = pts.shape[0]
@@ -493,7 +501,7 @@ class FieldFn(torch.autograd.Function):
                 feat = torch.empty(0, dtype=torch.uint8, device=pts.device)
         else:
             feat, keep = hash_encode_fwd(grid, [t.detach() for t in tables], pts, qparams)
-            out = mlp_fwd(w, feat, dirs=dirs, samples_per_ray=S, act_q=act_q, keep=keep, mode=ctx.mode)
+            out = mlp_fwd(w, feat, dirs=dirs, samples_per_ray=S, act_q=act_q, keep=keep, mode=_EXP_FWD or ctx.mode)
         ctx.grid, ctx.S, ctx.act_q, ctx.keys, ctx.n_tables = grid, S, act_q, keys, n_tables
         ctx.save_for_backward(pts, dirs, feat, keep, *params)
         return out
@@ -530,7 +538,8 @@ class FieldFn(torch.autograd.Function):
                      dptr(keep, torch.bool), dptr(dout), pts.shape[0], ctypes.byref(gs), dptr(wsp, torch.uint8),
                      wsp.numel(), stream())
             return (None,) * (8 + ctx.n_tables) + tuple(None if k in direct else dw[k] for k in ctx.keys)
-        dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep, mode=ctx.mode)
+        dfeat, _, dw = mlp_bwd(w, feat, dout, dirs=dirs, samples_per_ray=ctx.S, act_q=ctx.act_q, keep=keep,
+                               mode=_EXP_BWD or ctx.mode)
         if any(ctx.needs_input_grad[8:8 + ctx.n_tables]):
             flat = table_grad_buffer(tables)
             hash_encode_bwd(ctx.grid, list(flat.unbind(0)), pts, dfeat)

@@ -12,7 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-N_RAYS, STEPS, LOG2T = 4096, 300, 17
+N_RAYS, STEPS, LOG2T = 4096, 600, 17
 
 
 def _scene():
@@ -20,23 +20,29 @@ def _scene():
     return synthetic.blender_scene(200, 200, n_views=20)
 
 
-def _train(mode, steps, scene):
+def _train(mode, steps, scene, perturb=0.0, seed=0):
     import indoor_nerf_b200 as pn
     from indoor_nerf_b200 import model as pmodel, synthetic
     from indoor_nerf_b200.trainer import Trainer
     dev = torch.device("cuda", 0)
     a = pmodel.default_args(bounding_box=scene["bounding_box"], lrate=0.01, log2_hashmap_size=LOG2T)
-    torch.manual_seed(0)
+    torch.manual_seed(seed)
     kw, _, _, _, opt = pmodel.create_nerf(a, device=dev)
+    if perturb:
+        # an fp32-rounding-level nudge of the initial tables (relative 1e-6): how far does the SAME arithmetic drift?
+        g = torch.Generator(device=dev).manual_seed(99)
+        with torch.no_grad():
+            st = kw["embed_fn"].table_storage
+            st.mul_(1.0 + perturb * torch.randn(st.shape, device=dev, generator=g))
     tr = Trainer(a, kw, opt, scene["H"], scene["W"], scene["K"], scene["near"], scene["far"])
     init = ([e.weight.detach().clone() for e in kw["embed_fn"].embeddings],
             [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in (kw["network_fn"], kw["network_fine"])])
     pn.set_mlp_mode(mode)
     losses, psnrs = [], []
     try:
-        torch.manual_seed(1)
+        torch.manual_seed(1 + seed)
         for i in range(steps):
-            r, t = synthetic.ray_batch(scene, N_RAYS, seed=i, device=dev)
+            r, t = synthetic.ray_batch(scene, N_RAYS, seed=i + 100000 * seed, device=dev)
             loss, psnr = tr.step(r, t)
             losses.append(loss)
             psnrs.append(psnr)
@@ -65,36 +71,47 @@ def _train_oracle(steps, scene, init):
     return np.array(losses)
 
 
+SEEDS = (0, 1, 2, 3, 4, 5)
+WINDOWS = ((40, 80), (80, 150), (150, 250), (250, 400), (400, 500), (500, 600))
+
+
 def test_training_trajectories_fp32_bf16_oracle():
     scene = _scene()
-    l32, p32, init = _train("fp32", STEPS, scene)
-    l16, p16, init16 = _train("bf16", STEPS, scene)
-    assert all(torch.equal(a, b) for a, b in zip(init[0], init16[0]))          # same initial tables in both runs
+    runs = {m: [_train(m, STEPS, scene, seed=sd) for sd in SEEDS] for m in ("fp32", "bf16")}
+    l32, p32, init = runs["fp32"][0]
+    l16, p16, init16 = runs["bf16"][0]
+    assert all(torch.equal(a, b) for a, b in zip(init[0], init16[0]))          # same initial tables in both modes
     lo = _train_oracle(12, scene, init)
-    assert np.isfinite(l32).all() and np.isfinite(l16).all() and np.isfinite(lo).all()
+    for m in runs:
+        for l, p, _ in runs[m]:
+            assert np.isfinite(l).all() and np.isfinite(p).all()
 
     # (1) fp32 mode vs the oracle: same parameters, same draws (t_rand, u, TV cube origins in the same RNG order) ->
     #     the loss of every early iteration agrees to fp32-accumulation level before the trajectories decorrelate
     rel = np.abs(l32[:12] - lo) / lo
-    print("fp32 mode vs oracle, first 12 losses: rel diff", np.round(rel, 7))
+    print("fp32 mode vs oracle, first 12 losses: rel diff", ["%.1e" % r for r in rel])
     assert rel[0] < 2e-5 and rel[:4].max() < 2e-4 and rel.max() < 5e-3, rel
 
-    # (2) bf16 mode vs fp32 mode: first step within the op-level bar, then the same learning curve
+    # (2) bf16 mode vs fp32 mode.  First iteration: the op-level bar.  After that NeRF optimisation is chaotic: measured on
+    #     this scene, two fp32 runs whose initial tables differ by 1e-6 relative are 0.2-0.7 dB apart per window, and the
+    #     seed-to-seed spread of the PSNR at a fixed iteration is ~1 dB in EITHER mode (one seed alone had bf16 1.6 dB
+    #     behind, the next 1.2 dB ahead).  Equivalence is therefore a statement about the two DISTRIBUTIONS: over six
+    #     seeds (same seeds, batches and draws for both modes) the mean learning curves must coincide within the
+    #     standard error of their paired difference, in every window, and the bf16 mode must not be behind at the end.
     assert abs(l16[0] - l32[0]) / l32[0] < 2e-3
-    sm = lambda x, a, b: float(np.mean(x[a:b]))
-    rows = []
-    for a, b in ((20, 40), (40, 80), (80, 150), (150, 220), (220, 300)):
-        rows.append((a, b, sm(p32, a, b), sm(p16, a, b), sm(l32, a, b), sm(l16, a, b)))
-    print("window  psnr fp32  psnr bf16 | loss fp32  loss bf16")
-    for r in rows:
-        print("%3d-%3d  %8.3f  %8.3f | %.5f  %.5f" % r)
-    for a, b, q32, q16, m32, m16 in rows:
-        assert abs(q16 - q32) < 0.35, ("PSNR windows differ", a, b, q32, q16)          # dB, mean over the window
-        assert abs(m16 - m32) / m32 < 0.08, ("loss windows differ", a, b, m32, m16)
-    # both actually learn: > 6 dB over the first-iteration PSNR by the end
-    assert sm(p32, 250, 300) - p32[0] > 6.0 and sm(p16, 250, 300) - p16[0] > 6.0, (p32[0], sm(p32, 250, 300), sm(p16, 250, 300))
-    # and the bf16 run is not systematically worse: final-window PSNR within 0.25 dB
-    assert sm(p16, 250, 300) > sm(p32, 250, 300) - 0.25
+    P = {m: np.array([[float(np.mean(p[a:b])) for a, b in WINDOWS] for _, p, _ in runs[m]]) for m in runs}   # [seed, window]
+    diff = P["bf16"] - P["fp32"]
+    mean32, mean16 = P["fp32"].mean(0), P["bf16"].mean(0)
+    mdiff, se = diff.mean(0), diff.std(0, ddof=1) / np.sqrt(len(SEEDS))
+    print("window    mean psnr fp32  mean psnr bf16   paired diff +- s.e.   (dB, %d seeds)" % len(SEEDS))
+    for (a, b), x, y, d, e in zip(WINDOWS, mean32, mean16, mdiff, se):
+        print("%3d-%3d   %10.3f      %10.3f      %+7.3f +- %.3f" % (a, b, x, y, d, e))
+    print("final window per seed, fp32:", np.round(P["fp32"][:, -1], 2), " bf16:", np.round(P["bf16"][:, -1], 2))
+    for (a, b), d, e in zip(WINDOWS, mdiff, se):
+        assert abs(d) < max(0.5, 2.5 * e), ("mean learning curves differ", a, b, d, e)
+    # every run of either mode learns (> 12 dB over the first-iteration PSNR), and the bf16 mean is not behind at the end
+    assert (P["fp32"][:, -1] - p32[0] > 12.0).all() and (P["bf16"][:, -1] - p16[0] > 12.0).all()
+    assert mean16[-1] > mean32[-1] - 0.5, (mean32[-1], mean16[-1])
 
 
 def test_resume_continues_learning_rate_and_tv_cutoff():
