@@ -116,6 +116,33 @@ PN_HD uint32_t corner_index(const HashGridDev &G, const Cell &c, int corner) {
   return (hx ^ hy ^ hz) & G.mask;
 }
 
+// The 8 corner rows of a voxel, e0[k] / e1[k] = the two features of corner k = 4*dx + 2*dy + dz.  Corners k and k+4 differ
+// only in x (prime 1): when the voxel's x index is even their rows are h and h ^ 1, i.e. ONE aligned 16-byte entry pair,
+// fetched with one load instead of two.  A scattered gather costs the LSU one wavefront per distinct line it touches
+// whatever the access width, and the gather is bound by exactly that (ncu, round 2: LSU data pipe 78 % busy, 4.5
+// wavefronts per 8-byte gather instruction), so pairing removes a quarter of them.  Values are bit-identical.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void gather8(const HashGridDev &G, const float2 *__restrict__ tab, const Cell &c, float e0[8],
+                                        float e1[8]) {
+  if ((c.hx0 & 1u) == 0u) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i0 = corner_index(G, c, k);                        // dx = 0 row; the dx = 1 row is i0 ^ 1
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(tab) + (i0 >> 1));
+      const bool odd = (i0 & 1u) != 0u;
+      e0[k] = odd ? v.z : v.x;      e1[k] = odd ? v.w : v.y;
+      e0[k + 4] = odd ? v.x : v.z;  e1[k + 4] = odd ? v.y : v.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 e = __ldg(tab + corner_index(G, c, k));
+      e0[k] = e.x; e1[k] = e.y;
+    }
+  }
+}
+#endif
+
 // LearnedBitwidthQuantizer.forward on one value (quantization.py:177-187); q = row of PN_QROW floats.
 PN_HD float fake_quant(float x, float scale, float denom, float zp, float qmin, float qmax, bool train_form) {
   float q = rintf(pn_add(pn_div(x, denom), zp));             // torch.round = half to even

@@ -44,13 +44,8 @@ hash_fwd_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ T
     for (int l = 0; l < G.n_levels; ++l) {
       Cell c;
       point_cell(G, l, xv, c);
-      const float2 *__restrict__ tab = T.t[l];
-      float2 e[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) e[k] = __ldg(tab + corner_index(G, c, k));
       float e0[8], e1[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { e0[k] = e[k].x; e1[k] = e[k].y; }
+      gather8(G, T.t[l], c, e0, e1);
       if (QUANT) {
         const float *q = qparams + l * PN_QROW;
         if (q[5] != 0.f) {
@@ -284,7 +279,9 @@ extern "C" int pn_hash_encode_fwd(const pn_hash_grid *grid, const float *const *
   TablePtrs T;
   for (int l = 0; l < PN_MAX_LEVELS; ++l)
     T.t[l] = reinterpret_cast<const float2 *>(tables[l < grid->n_levels ? l : 0]);
-  for (int l = 0; l < grid->n_levels; ++l) PN_REQUIRE(tables[l] != nullptr, PN_EINVAL, "tables[%d] is NULL", l);
+  for (int l = 0; l < grid->n_levels; ++l)
+    PN_REQUIRE(tables[l] != nullptr && ((uintptr_t)tables[l] & 15) == 0, PN_EINVAL,
+               "tables[%d] is NULL or not 16-byte aligned (x-adjacent corner rows are fetched as one 16-byte pair)", l);
   const int blocks = hash_blocks(n_points, kHashThreads, 16);
   if (qparams)
     hash_fwd_kernel<true><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, qparams, x, n_points, feat, keep);
@@ -320,7 +317,7 @@ extern "C" int pn_hash_encode_bwd(const pn_hash_grid *grid, float *const *dtable
   for (int l = 0; l < PN_MAX_LEVELS; ++l) D.t[l] = reinterpret_cast<float2 *>(dtables[l < grid->n_levels ? l : 0]);
   for (int l = 0; l < grid->n_levels; ++l)
     PN_REQUIRE(dtables[l] != nullptr && ((uintptr_t)dtables[l] & 15) == 0, PN_EINVAL,
-               "dtables[%d] is NULL or not 16-byte aligned (paired 16-byte reductions)", l);
+               "dtables[%d] is NULL or not 16-byte aligned", l);
   const int blocks = hash_blocks(n_points, kHashThreads, 16);
   hash_bwd_kernel<<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, D, x, dfeat, n_points);
   count_launch();

@@ -255,9 +255,7 @@ __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, con
         if (SRC == SRC_PACKED) {
 packed_gather8<false>(F->PK, l, F->G, c, e0, e1);
         } else {
-          const float2 *__restrict__ tab = F->T.t[l];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { const float2 e = __ldg(tab + corner_index(F->G, c, k)); e0[k] = e.x; e1[k] = e.y; }
+          gather8(F->G, F->T.t[l], c, e0, e1);
         }
         if (SRC == SRC_HASH && F->qparams) {
           const float *q = F->qparams + l * PN_QROW;
@@ -1433,7 +1431,7 @@ field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
 // (the standalone scatter kernel reaches 71 % issue utilisation with 32 warps/SM), not a place in the chain.
 // ------------------------------------------------------------------------------------------------------
 #ifndef PN_V4_SCATTER_WARPS
-#define PN_V4_SCATTER_WARPS 3
+#define PN_V4_SCATTER_WARPS 7
 #endif
 constexpr int kV4ScatterWarps = PN_V4_SCATTER_WARPS;                    // 3 (12 warps per CTA) or 7 (16 warps)
 constexpr int kV4Threads = kTcThreads + 32 + 32 * kV4ScatterWarps;
@@ -1443,7 +1441,13 @@ constexpr int kV4EpiRegs = kV4ScatterWarps == 3 ? 88 : 80, kV4AuxRegs = kV4Scatt
 constexpr int kRingSlots = 4;
 static_assert(kV4ScatterWarps == 3 || kV4ScatterWarps == 7, "warps 8.. must fill whole warpgroups (setmaxnreg)");
 
-template <bool NORMALS>
+// SEG: which scatter the scatter warps run — true: a lane walks 4 consecutive samples serially per level
+// (scatter_segment, ring slot laid out [level][row]); false: a lane owns one sample and runs are summed with the shuffle
+// tree (scatter_level, ring slot [row][level]).  Measured in the training step (round 2): with 192 sorted samples per ray
+// (fine pass) consecutive samples share voxels at most levels and SEG wins (5.41 -> 5.19 ms); with 64 samples per ray
+// (coarse pass) they rarely do and the 4-sample serial loop only costs parallelism (2.25 -> 2.67 ms) — so the launcher
+// picks SEG by samples_per_ray.
+template <bool NORMALS, bool SEG>
 __global__ void __launch_bounds__(kV4Threads, 2)
 field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout, const pn_mlp_grads G,
                   float *__restrict__ ring) {
@@ -1521,6 +1525,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   }
 
   if (warp >= 9) {
+    if (SEG) {
     // ---------------- scatter role: kV4ScatterWarps warps; work item = (tile, 4 levels), taken round-robin -------------
     // A lane owns 4 CONSECUTIVE samples of the tile (rows 4*lane .. +3) and walks them serially per level
     // (scatter_segment): consecutive samples of a ray that share a voxel are summed in registers, no shuffles.
@@ -1548,6 +1553,38 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ring_empty[slot]);
+    }
+    } else {
+    // ---------------- scatter role: kV4ScatterWarps warps, work item = (tile, quarter), taken round-robin ----------------
+    const int sw = warp - 9;
+    const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;      // tiles this CTA walks
+    for (int64_t item = sw; item < my_tiles * 4; item += kV4ScatterWarps) {
+      const int64_t n = item >> 2;
+      const int qd = (int)(item & 3), slot = (int)(n % kRingSlots);
+      const int64_t pt = (blockIdx.x + n * gridDim.x) * kTcTile + qd * 32 + lane;
+      const bool valid = pt < A.in.n_points;
+      float xv[3] = {0.f, 0.f, 0.f};
+      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
+      mbar_wait(&ring_full[slot], (uint32_t)(n / kRingSlots) & 1);
+      // rows of this quarter with a gradient (published by the epilogue warps with the tile); 32 gradient-free samples
+      // (empty space, occluded samples) cost one shared-memory read
+      const uint32_t rows_nz = (ring_nz[slot][qd][0] | ring_nz[slot][qd][1]) & __ballot_sync(0xffffffffu, valid);
+      if (rows_nz != 0u && !(F.debug & 1)) {
+        const bool act = (rows_nz >> lane) & 1u;
+        // two values per level straight from the ring row (L2 / L1 hits), the next level's in flight during this one's
+        // scatter: no local-memory staging (the 107 KB x 2 of shared memory leave the SM almost no L1 for stack traffic)
+        const float2 *row = reinterpret_cast<const float2 *>(cta_ring + ((size_t)slot * kTcTile + qd * 32 + lane) * 32);
+        float2 gc = act ? row[0] : make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int l = 0; l < F.G.n_levels; ++l) {
+          const float2 gn = (act && l + 1 < F.G.n_levels) ? row[l + 1] : make_float2(0.f, 0.f);
+          scatter_level<false>(F.G, F.D.t[l], l, xv, gc.x, gc.y, lane);
+          gc = gn;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ring_empty[slot]);
+    }
     }
     __syncthreads();
     return;
@@ -1719,13 +1756,23 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       float v[16];
       tmem_ld16(lane_addr + TM_D1 + half * 16, v);
       tmem_ld_wait();
-      // slot layout [level][row] float2 (a warp stores 256 contiguous bytes per level)
-      float2 *col = reinterpret_cast<float2 *>(cta_ring + (size_t)slot * (kTcTile * 32)) + (size_t)(half * 8) * kTcTile + p;
       bool nzr = false;
+      if (SEG) {
+        // slot layout [level][row] float2 (a warp stores 256 contiguous bytes per level)
+        float2 *col = reinterpret_cast<float2 *>(cta_ring + (size_t)slot * (kTcTile * 32)) + (size_t)(half * 8) * kTcTile + p;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        col[(size_t)i * kTcTile] = make_float2(v[2 * i], v[2 * i + 1]);
-        nzr = nzr || v[2 * i] != 0.f || v[2 * i + 1] != 0.f;
+        for (int i = 0; i < 8; ++i) {
+          col[(size_t)i * kTcTile] = make_float2(v[2 * i], v[2 * i + 1]);
+          nzr = nzr || v[2 * i] != 0.f || v[2 * i + 1] != 0.f;
+        }
+      } else {
+        // slot layout [row][level] float2: this thread's half row is 64 contiguous bytes
+        float4 *row = reinterpret_cast<float4 *>(cta_ring + ((size_t)slot * kTcTile + p) * 32 + half * 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          row[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          nzr = nzr || v[4 * c] != 0.f || v[4 * c + 1] != 0.f || v[4 * c + 2] != 0.f || v[4 * c + 3] != 0.f;
+        }
       }
       const uint32_t nzm = __ballot_sync(0xffffffffu, nzr && valid);
       fence_before_sync();                             // the tcgen05.ld above precedes the next tile's first MMA (via `ready`)
@@ -1880,8 +1927,10 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
@@ -1893,8 +1942,17 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
     PN_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= field_bwd_workspace_bytes(), PN_EINVAL,
                "pn_field_bwd_bf16 needs a 16-byte aligned workspace of pn_field_bwd_workspace_bytes() = %lld bytes (got %lld)",
                (long long)field_bwd_workspace_bytes(), (long long)workspace_bytes);
-    if (A.normals) field_bwd4_kernel<true><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, reinterpret_cast<float *>(workspace));
-    else field_bwd4_kernel<false><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, reinterpret_cast<float *>(workspace));
+    static int seg_min = -1;                     // PN_SCATTER_SEG_MIN: samples per ray from which the serial segment scatter runs
+    if (seg_min < 0) {
+      const char *e = getenv("PN_SCATTER_SEG_MIN");
+      seg_min = e ? atoi(e) : 128;
+    }
+    const bool seg = A.in.samples_per_ray >= seg_min;
+    float *ring = reinterpret_cast<float *>(workspace);
+    if (A.normals && seg) field_bwd4_kernel<true, true><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
+    else if (A.normals) field_bwd4_kernel<true, false><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
+    else if (seg) field_bwd4_kernel<false, true><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
+    else field_bwd4_kernel<false, false><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
   } else if (fused && bwd_variant() == 2) {
     field_bwd3_kernel<<<blocks, kV3Threads, smem, st>>>(A, F, dout, dw);
   } else if (fused && bwd_variant() == 1)
@@ -1948,7 +2006,8 @@ static int fill_field(FieldArgs &F, const pn_hash_grid *grid, const float *const
   for (int l = 0; l < PN_MAX_LEVELS; ++l) {
     F.T.t[l] = tables ? reinterpret_cast<const float2 *>(tables[l]) : nullptr;
     F.D.t[l] = dtables ? reinterpret_cast<float2 *>(dtables[l]) : nullptr;
-    PN_REQUIRE(!tables || tables[l], PN_EINVAL, "tables[%d] is NULL", l);
+    PN_REQUIRE(!tables || (tables[l] && ((uintptr_t)tables[l] & 15) == 0), PN_EINVAL,
+               "tables[%d] is NULL or not 16-byte aligned", l);
     PN_REQUIRE(!dtables || (dtables[l] && ((uintptr_t)dtables[l] & 15) == 0), PN_EINVAL,
                "dtables[%d] is NULL or not 16-byte aligned", l);
   }
