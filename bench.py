@@ -733,7 +733,7 @@ def run_ours(args):
             line["workloads"] = wls
 
     # ---- rank-0 legs ---------------------------------------------------------------------------------------------------
-    if rank == 0 and extras and args.workload == "chair":
+    if rank == 0 and world == 1 and extras and args.workload == "chair":      # single-GPU legs: not repeated at N > 1
         r, t = wl["pool_dev"][0]
         with torch.no_grad():
             z = torch.sort(2.0 + 4.0 * torch.rand(n_rays, 192, device=dev), -1)[0]

@@ -11,6 +11,8 @@
 //   hash_encoding.py:64   w = (x - vmin) / (vmax - vmin)      with the UNclamped x (:103)
 //   hash_encoding.py:68-78  lerp along x (corner pairs c, c+4), then y, then z
 #pragma once
+#include <stdlib.h>
+
 #include "pn_common.cuh"
 
 namespace pn {
@@ -22,6 +24,7 @@ struct HashGridDev {
   float rg[PN_MAX_LEVELS][3];  // 1 / g (bf16 paths only)
   int n_levels;
   uint32_t mask;
+  int pair_gather;             // fetch x-adjacent corner rows as one 16-byte pair (table set larger than the L2)
 };
 
 // utils.py:107  grid_size = (box_max - box_min) / resolution
@@ -36,6 +39,15 @@ inline HashGridDev make_grid_dev(const pn_hash_grid &h) {
     }
   G.n_levels = h.n_levels;
   G.mask = (1u << h.log2_hashmap_size) - 1u;
+  // Measured (round 2, 12.6 M ray-ordered points): T = 2^22 (512 MiB of tables, DRAM-bound) 2.92 -> 2.57 ms with paired
+  // loads; T = 2^19 (64 MiB, L2-resident) 1.76 -> 1.84 ms and the fused forward 2.45 -> 2.75 ms: with every sector an L2
+  // hit the even / odd divergence costs more than the saved sectors.  PN_PAIR_GATHER=0|1 overrides.
+  static int force = -2;
+  if (force == -2) {
+    const char *e = getenv("PN_PAIR_GATHER");
+    force = e ? atoi(e) : -1;
+  }
+  G.pair_gather = force >= 0 ? force : (((size_t)h.n_levels << h.log2_hashmap_size) * 8 > (size_t)100 * 1024 * 1024);
   return G;
 }
 
@@ -119,12 +131,12 @@ PN_HD uint32_t corner_index(const HashGridDev &G, const Cell &c, int corner) {
 // The 8 corner rows of a voxel, e0[k] / e1[k] = the two features of corner k = 4*dx + 2*dy + dz.  Corners k and k+4 differ
 // only in x (prime 1): when the voxel's x index is even their rows are h and h ^ 1, i.e. ONE aligned 16-byte entry pair,
 // fetched with one load instead of two.  A scattered gather costs the LSU one wavefront per distinct line it touches
-// whatever the access width, and the gather is bound by exactly that (ncu, round 2: LSU data pipe 78 % busy, 4.5
-// wavefronts per 8-byte gather instruction), so pairing removes a quarter of them.  Values are bit-identical.
+// whatever the access width, and a gather that misses the L2 moves a 32-byte DRAM sector per row: pairing removes a
+// quarter of both.  Only used when the table set does not fit the L2 (G.pair_gather).  Values are bit-identical.
 #if defined(__CUDACC__)
 __device__ __forceinline__ void gather8(const HashGridDev &G, const float2 *__restrict__ tab, const Cell &c, float e0[8],
                                         float e1[8]) {
-  if ((c.hx0 & 1u) == 0u) {
+  if (G.pair_gather && (c.hx0 & 1u) == 0u) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t i0 = corner_index(G, c, k);                        // dx = 0 row; the dx = 1 row is i0 ^ 1
