@@ -181,10 +181,10 @@ int64_t pn_field_bwd_workspace_bytes(void);
  * hardware.  D is the raw [128 lanes][N] accumulator. */
 int pn_tc_selftest(const int32_t *cfg, const float *A, const float *B, float *D, pn_stream_t stream);
 
-/* Diagnostic: install (buf != NULL) or remove a device buffer of 3 * cap_per_thread int64 into which the fused
- * backward kernel's CTA 0 writes clock64() marks at the boundaries of its MMA -> epilogue rounds (thread 0 in
- * [0, cap), thread 160 in [cap, 2 cap), the MMA warp's elected lane in [2 cap, 3 cap)): scripts/timeline_rounds.py
- * turns them into a per-round latency table.  Never set in production; the kernels test one pointer per mark. */
+/* Diagnostic: install (buf != NULL) or remove a device buffer of 3 * cap_per_thread int64 into which CTA 0 of the
+ * single-role fused backward (PN_FIELD_BWD=v1) writes clock64() marks at the boundaries of its MMA -> epilogue rounds
+ * (thread 0 = the MMA issuer in [0, cap), thread 160 in [cap, 2 cap); the third row is spare): scripts/timeline_rounds.py
+ * turns them into a per-round latency table.  Never set in production; the kernel tests one pointer per mark. */
 int pn_debug_timeline(int64_t *buf, int64_t cap_per_thread);
 
 /* ---- volume rendering ---------------------------------------------------------------------------- */

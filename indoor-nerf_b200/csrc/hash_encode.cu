@@ -45,7 +45,7 @@ hash_fwd_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ T
       Cell c;
       point_cell(G, l, xv, c);
       float e0[8], e1[8];
-      gather8(G, T.t[l], c, e0, e1);
+      gather8<true>(G, T.t[l], c, e0, e1);
       if (QUANT) {
         const float *q = qparams + l * PN_QROW;
         if (q[5] != 0.f) {

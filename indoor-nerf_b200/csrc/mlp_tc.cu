@@ -136,14 +136,14 @@ struct FieldArgs {
   int scatter_split;    // backward: half 0 scatters levels [0, split), half 1 the rest
   int debug;            // PN_DEBUG_FLAGS (measurement only): 1 = skip the scatter work, 2 = skip the gather work
   int sc_direct, sc_maxlen;   // scatter_level tuning (PN_SCATTER_DIRECT, PN_SCATTER_MAXLEN)
-  long long *tlog;      // pn_debug_timeline buffer: [3 threads][tlog_cap] clock64 marks, or NULL
+  long long *tlog;      // pn_debug_timeline buffer: [2 threads][tlog_cap] (+1 spare row) clock64 marks, or NULL
   int tlog_cap;
   PackedDev PK;         // SRC_PACKED: tables as integer codes (inference)
 };
 
-// Diagnostic timeline (pn_debug_timeline): when a log buffer is installed, two threads of CTA 0 — thread 0 (the MMA
-// issuer) and thread 160 (an ordinary epilogue thread) — write clock64() at the marked points of every round of their
-// first tiles.  One predictable branch per mark otherwise; never set in production runs.
+// Diagnostic timeline (pn_debug_timeline): when a log buffer is installed, two threads of CTA 0 of the single-role
+// backward — thread 0 (the MMA issuer) and thread 160 (an ordinary epilogue thread) — write clock64() at the marked
+// points of every round of their first tiles.  One predictable branch per mark otherwise; never set in production runs.
 struct TLog {
   long long *p;
   int i, cap;
@@ -255,7 +255,7 @@ __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, con
         if (SRC == SRC_PACKED) {
 packed_gather8<false>(F->PK, l, F->G, c, e0, e1);
         } else {
-          gather8(F->G, F->T.t[l], c, e0, e1);
+          gather8<false>(F->G, F->T.t[l], c, e0, e1);
         }
         if (SRC == SRC_HASH && F->qparams) {
           const float *q = F->qparams + l * PN_QROW;
@@ -509,202 +509,6 @@ mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__
   if (warp == 0) tmem_dealloc(tmem, TM_FWD_COLS);
 }
 
-// ------------------------------------------------------------------------------------------------------
-// Warp-specialised fused forward (pn_field_fwd_bf16): 8 MLP warps + GW gather warps per CTA, 2 CTAs per SM.
-//   gather warps (producers): evaluate the hash grid (and SH, keep mask, saved feature tile) of tile n+1 straight into
-//     the second A0 / CIN operand buffer while
-//   MLP warps (consumers) run the five MMA -> epilogue rounds of tile n.
-// full[b]  : 32*GW gather threads arrive after fence.proxy.async   -> gates the tile's first MMA (thread 0)
-// empty[b] : tcgen05.commit after the R3 MMAs (last readers of A0[b] / CIN[b]) -> gates the gather of tile n+2
-// In the single-role kernel the gather (L2 latency) and the round chain (MMA latency) of a tile are serial inside a
-// CTA: 2.7 ms per 12.6 M points against 1.7 ms (gather alone) and 1.6 ms (MLP alone).
-// ------------------------------------------------------------------------------------------------------
-struct FW {
-  static constexpr int A0B = TS::FWD_END;               // second [128 x 32] feature buffer
-  static constexpr int CINB = A0B + 128 * 32 * 2;       // second [128 x 32] colour-input buffer
-  static constexpr int END = CINB + 128 * 32 * 2;
-};
-
-template <int GW>
-__global__ void __launch_bounds__(kTcThreads + 32 * GW, 2)
-field_fwd_ws_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__restrict__ out) {
-  static_assert(GW == 4 || GW == 8, "4 gather warps (16 levels per thread) or 8 (8 levels per thread)");
-  constexpr int LPT = 16 / (GW / 4);                    // levels per gather thread
-  constexpr int kAuxRegs = GW == 4 ? 64 : 48, kMlpRegs = GW == 4 ? 88 : 80;
-  static_assert(256 * kMlpRegs + 32 * GW * kAuxRegs <= 65536 / 2, "register file at 2 CTAs/SM");
-  extern __shared__ __align__(128) uint8_t sm[];
-  __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t bar, full[2], empty[2];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  load_all_weights(sm, A);
-  if (warp == 0) tmem_alloc(&tmem_slot, TM_FWD_COLS);
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    mbar_init(&full[0], 32 * GW); mbar_init(&full[1], 32 * GW);
-    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_fence_init();
-  }
-  fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
-
-  if (warp >= 8) {
-    // ---------------- gather role ----------------
-    setmaxnreg_dec<kAuxRegs>();
-    const int gw = warp - 8, gp = (gw & 3) * 32 + lane, lh = gw >> 2;
-    const int l_first = lh * LPT;
-    const bool quant = F.qparams != nullptr;
-    uint32_t n = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      const int buf = n & 1;
-      uint8_t *a0 = sm + (buf ? FW::A0B : TS::A0), *cin = sm + (buf ? FW::CINB : TS::CIN);
-      const int64_t pt = tile * kTcTile + gp;
-      const bool valid = pt < A.in.n_points;
-      float xv[3] = {0.f, 0.f, 0.f};
-      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
-      // PIPE (4 gather warps, 64 registers): software pipeline over the levels — the 8 gathers of level l+1 are in
-      // flight while level l is interpolated.  With 8 gather warps (48 registers) the other warps cover the latency.
-      constexpr bool PIPE = GW == 4;
-      Cell c;
-      float2 e[8];
-      if (F.debug & 2) {
-        if (n >= 2) mbar_wait(&empty[buf], ((n >> 1) - 1) & 1);
-        for (int i = 0; i < LPT; i += 4)
-          *reinterpret_cast<uint4 *>(a0 + chunk_off(gp, (l_first + i) >> 2, 4)) = make_uint4(0u, 0u, 0u, 0u);
-        if (lh == 0) {
-          *reinterpret_cast<uint4 *>(cin + chunk_off(gp, 0, 4)) = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4 *>(cin + chunk_off(gp, 1, 4)) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        fence_async_smem();
-        mbar_arrive(&full[buf]);
-        continue;
-      }
-      if (PIPE) {
-        point_cell<false>(F.G, l_first, xv, c);
-        const float2 *__restrict__ tab = F.T.t[l_first];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) e[k] = __ldg(tab + corner_index(F.G, c, k));
-      }
-      if (n >= 2) mbar_wait(&empty[buf], ((n >> 1) - 1) & 1);    // tile n-2's MMAs have read this buffer
-      uint32_t word[4];
-#pragma unroll 4
-      for (int i = 0; i < LPT; ++i) {
-        const int l = l_first + i;
-        Cell cn;
-        float2 en[8];
-        if (PIPE) {
-          if (i + 1 < LPT) {
-            point_cell<false>(F.G, l + 1, xv, cn);
-            const float2 *__restrict__ tab = F.T.t[l + 1];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) en[k] = __ldg(tab + corner_index(F.G, cn, k));
-          }
-        } else {
-          point_cell<false>(F.G, l, xv, c);
-          const float2 *__restrict__ tab = F.T.t[l];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) e[k] = __ldg(tab + corner_index(F.G, c, k));
-        }
-        float e0[8], e1[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { e0[k] = e[k].x; e1[k] = e[k].y; }
-        if (quant) {
-          const float *q = F.qparams + l * PN_QROW;
-          if (q[5] != 0.f) {
-            const float scale = q[0], rdenom = 1.0f / q[1], zp = q[2], qmin = q[3], qmax = q[4];
-            const bool train_form = q[6] != 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              e0[k] = fake_quant_fast(e0[k], scale, rdenom, zp, qmin, qmax, train_form);
-              e1[k] = fake_quant_fast(e1[k], scale, rdenom, zp, qmin, qmax, train_form);
-            }
-          }
-        }
-        const float f0 = valid ? trilerp_fast(e0, c.w) : 0.f, f1 = valid ? trilerp_fast(e1, c.w) : 0.f;
-        word[i & 3] = pack_bf16(f0, f1);
-        if ((i & 3) == 3) {                                       // 4 levels = one 16-byte chunk of the operand row
-          const uint32_t off = chunk_off(gp, l >> 2, 4);
-          const uint4 u = make_uint4(word[0], word[1], word[2], word[3]);
-          *reinterpret_cast<uint4 *>(a0 + off) = u;
-          if (F.featb) F.featb[tile * 512 + (off >> 4)] = u;      // the backward's operand tile, same layout
-        }
-        if (PIPE && i + 1 < LPT) {
-          c = cn;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) e[k] = en[k];
-        }
-      }
-      if (lh == 0) {
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = 0.f;
-        if (valid) {
-          const int64_t r = pt / A.in.samples_per_ray;
-          sh4(__ldg(A.in.dirs + 3 * r), __ldg(A.in.dirs + 3 * r + 1), __ldg(A.in.dirs + 3 * r + 2), o);
-          if (F.keep_out) F.keep_out[pt] = point_keep(F.G, xv) ? 1 : 0;
-        }
-        st_chunk(cin, chunk_off(gp, 0, 4), o);
-        st_chunk(cin, chunk_off(gp, 1, 4), o + 8);
-      }
-      fence_async_smem();
-      mbar_arrive(&full[buf]);
-    }
-    __syncthreads();                                    // the CTA-wide barrier before the TMEM release below
-    return;
-  }
-
-  // ---------------- MLP role ----------------
-  setmaxnreg_inc<kMlpRegs>();
-  const int p = tid & 127, half = tid >> 7;
-  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  uint32_t ph = 0;
-  float q[8];
-  const float *qrow = nullptr;
-  if (A.in.act_q) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
-    if (q[5] != 0.f) qrow = q;
-  }
-  uint32_t n = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-    const int buf = n & 1;
-    const int64_t base = tile * kTcTile;
-    const bool valid = base + p < A.in.n_points;
-    float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
-    uint32_t m;
-    tc_forward<false>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, m, &full[buf], (n >> 1) & 1,
-                      buf ? FW::A0B : TS::A0, buf ? FW::CINB : TS::CIN, &empty[buf]);
-    // R5: rgb = A2c C2^T
-    if (tid == 0) {
-      fence_after_sync();
-      issue(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_C2, 64), instr_desc(128, 16, 0, 0), 4, false);
-      mma_commit(&bar);
-    }
-    mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    if (half == 0) {
-      float v[16];
-      tmem_ld16(lane_addr + TM_D2, v);
-      tmem_ld_wait();
-      if (valid) {
-        const float xv[3] = {__ldg(F.pts + 3 * (base + p)), __ldg(F.pts + 3 * (base + p) + 1), __ldg(F.pts + 3 * (base + p) + 2)};
-        const bool kept = point_keep(F.G, xv);
-        float *o = out + (base + p) * A.C;
-        if (A.C == 4) {
-          *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], kept ? sigma : 0.f);
-        } else {
-          const float nn = fmaxf(sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]), 1e-12f);
-          o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = sigma;
-          o[4] = nraw[0] / nn; o[5] = nraw[1] / nn; o[6] = kept ? nraw[2] / nn : 0.f;
-        }
-      }
-    }
-    // no end-of-tile barrier: the next writer of D2 (R2 of the next tile) is issued behind the round barrier that
-    // follows R1's epilogue, which every thread reaches only after its reads above
-  }
-  fence_before_sync(); __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TM_FWD_COLS);
-}
-
 // masked in-place epilogue of an input-gradient GEMM, this thread's 32 columns:
 // tile row <- D * [tile row > 0] (or an explicit mask)
 __device__ __forceinline__ void epi_grad32(uint32_t taddr, uint8_t *tile, int p, int half, bool use_mask, uint32_t mask) {
@@ -750,59 +554,22 @@ __device__ __forceinline__ void flush_acc(uint32_t taddr, int ncols, bool owner,
   }
 }
 
-// Warp-specialised variant (WS = true, fused scatter only): the CTA has 4 more warps (8..11) that do nothing but the
-// hash-grid scatter.  Warp 8+q owns TMEM lane quarter q = the 32 points of the tile whose feature gradients the last
-// MMA of the tile (B5) leaves in D1[0,32).  B5 commits to `dx_full` as well; the scatter warp copies its 32 x 32
-// block of dX out of TMEM into registers / local memory, arrives on `dx_empty` (which gates the next tile's first
-// MMA, the next writer of D1) and then walks the 16 levels while warps 0-7 are already in the ten MMA -> epilogue
-// rounds of the next tile.  The MLP rounds are a latency chain (~1.3 k cycles per round, one tile per CTA in flight);
-// the scatter is pure issue work (~60 % of the kernel's instructions) — run side by side they fill each other's
-// stalls instead of alternating.
-constexpr int kWsThreads = kTcThreads + 128;
-constexpr int kWsMlpRegs = 96, kWsAuxRegs = 48;     // (256 * 96 + 128 * 48) = 384 * 80: the CTA's allocation at 2 CTAs/SM
-
-template <int SRC, bool WS>
-__global__ void __launch_bounds__(WS ? kWsThreads : kTcThreads, 2)
+template <int SRC>
+__global__ void __launch_bounds__(kTcThreads, 2)
 mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout,
                   float *__restrict__ dfeat, int64_t dfeat_stride, float *__restrict__ dsh, int64_t dsh_stride,
                   const pn_mlp_grads G) {
-  static_assert(!WS || SRC == SRC_TILE, "the warp-specialised backward is the fused field kernel");
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t bar, dx_full, dx_empty;
-  const int tid = threadIdx.x, p = tid & 127, half = (tid >> 7) & 1, warp = tid >> 5, lane = tid & 31;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, p = tid & 127, half = tid >> 7, warp = tid >> 5, lane = tid & 31;
   load_all_weights(sm, A);
   if (warp == 0) tmem_alloc(&tmem_slot, TM_BWD_COLS);
-  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&dx_full, 1); mbar_init(&dx_empty, 128); mbar_fence_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
-  if (WS && warp >= 8) {
-    // ---------------- scatter role ----------------
-    setmaxnreg_dec<kWsAuxRegs>();
-    uint32_t phs = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t pt = tile * kTcTile + (warp - 8) * 32 + lane;
-      const bool valid = pt < A.in.n_points;
-      float xv[3] = {0.f, 0.f, 0.f};
-      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
-      float g[32];                                   // indexed by the rolled level loop -> local memory (L1-resident)
-      mbar_wait(&dx_full, phs); phs ^= 1; fence_after_sync();
-      tmem_ld16(lane_addr + TM_D1, g);
-      tmem_ld16(lane_addr + TM_D1 + 16, g + 16);
-      tmem_ld_wait();
-      fence_before_sync();
-      mbar_arrive(&dx_empty);
-      if (F.debug & 1) continue;
-#pragma unroll 1
-      for (int l = 0; l < F.G.n_levels; ++l)
-        scatter_level<false>(F.G, F.D.t[l], l, xv, valid ? g[2 * l] : 0.f, valid ? g[2 * l + 1] : 0.f, lane);
-    }
-    __syncthreads();                                 // the CTA-wide barrier before the TMEM release below
-    return;
-  }
-  if (WS) setmaxnreg_inc<kWsMlpRegs>();
   uint32_t ph = 0, n_done = 0;
   TLog T = {nullptr, 0, F.tlog_cap};
   if (F.tlog && blockIdx.x == 0 && (tid == 0 || tid == 160)) T.p = F.tlog + (tid ? F.tlog_cap : 0);
@@ -831,9 +598,8 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     PN_ROUND_SYNC();
     float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
     uint32_t h1_mask;
-    // WS: tile n's first MMA overwrites D1, which holds tile n-1's dX until phase n-1 of dx_empty completes
-    tc_forward<true>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, h1_mask,
-                     (WS && n_done > 0) ? &dx_empty : nullptr, (n_done - 1) & 1, TS::A0, TS::CIN, nullptr, &T);
+    tc_forward<true>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, h1_mask, nullptr, 0, TS::A0, TS::CIN,
+                     nullptr, &T);
 
     // B0: cotangent tiles (half 0 owns the row-level values)
     if (half == 0) {
@@ -978,14 +744,11 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
       issue(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
       issue(tmem + TM_D1, k_major(sm + TS::A1, 64), mn_major(sm + TS::W_S0, 32), instr_desc(128, 32, 0, 1), 4, false);
       mma_commit(&bar);
-      if (WS) mma_commit(&dx_full);                    // the scatter warps' go-ahead: dX is complete in D1[0,32)
     }
     T.mark();
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
-    T.mark();  // (WS: A0 / A1 may be overwritten by the next tile from here)
-    if (WS) {
-      // nothing: warps 8-11 scatter this tile while this role moves on
-    } else if (SRC == SRC_TILE) {
+    T.mark();
+    if (SRC == SRC_TILE) {
       // Fused scatter.  A warp's 32 lanes are 32 consecutive samples, so the run-aggregated scatter applies
       // unchanged.  Half 0 scatters levels [0, split), half 1 the rest; each level's two gradients are read from
       // TMEM inside the loop so that the loop stays rolled (16 inlined copies of the scatter code thrashed the
@@ -1016,7 +779,7 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     T.mark();
     first = false;
     ++n_done;
-    if (!WS) { fence_before_sync(); mlp_sync(); }
+    fence_before_sync(); mlp_sync();
   }
   // flush the weight gradients (every MMA has completed: the last commit was waited on)
   fence_after_sync();
@@ -1047,20 +810,15 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
 
 
 // ------------------------------------------------------------------------------------------------------
-// Fused backward, third structure (pn_field_bwd_bf16, PN_FIELD_BWD=v3): three roles per CTA, 2 CTAs per SM.
-//   warps 0-7   epilogue: TMEM -> ReLU mask / bf16 -> operand tiles (thread = row x column half), as before
-//   warps 8-11  scatter : take the tile's dX out of TMEM and walk the 16 hash levels (as in the WS kernel)
-//   warp  12    MMA     : waits for `ready` (8 arrivals: one elected lane per epilogue warp), issues the round's
-//                         tcgen05.mma from warp-uniform control flow with precomputed descriptor words, commits to
-//                         `done`; between rounds it prefetches the next tile's inputs into L2.
-// What the clock64 timeline of the single-role kernel showed per 128-point tile (33 k cycles): 3.0 k waiting for the
-// saved feature tile and 2.4 k for the cotangent rows (DRAM latency, exposed once each), 6 k in thread 0 building
-// descriptors and issuing the 78 MMAs of a tile (~80 cycles each from a divergent branch), 16 k in the scatter; the MMAs
-// themselves and the epilogues are ~1 k and ~2 k.  Here the epilogue warps never issue or meet at a CTA barrier: they
-// arrive on `ready` and go straight to waiting on `done`.
+// Helpers of the three-role backward below: a dedicated MMA warp and per-warp mbarrier hand-offs.
+// What the clock64 timeline of the single-role kernel above showed per 128-point tile (33 k cycles,
+// profiles/r02_timeline_bwd_v1_ws_clock64.txt): 3.0 k waiting for the saved feature tile and 2.4 k inside the first
+// epilogue (an if-converted fake-quant, since fixed), 6 k in thread 0 building descriptors and issuing the 78 MMAs of a
+// tile (~80 cycles each from a divergent branch), 16 k in the scatter; the MMAs themselves and the epilogues are ~1 k and
+// ~2 k.  In the three-role kernel the MMA warp issues from warp-uniform control flow with precomputed descriptor words
+// (uniform datapath, ~20-40 cycles per MMA), prefetches the next tile's inputs into L2, and the epilogue warps never
+// issue or meet at a CTA barrier: they arrive on `ready` (one elected lane per warp) and go straight to waiting on `done`.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kV3Threads = kTcThreads + 128 + 32;
-constexpr int kV3EpiRegs = 80, kV3AuxRegs = 56;          // 256*80 + 128*56 + 32*72 = 416*72 (launch bound at 2 CTAs/SM)
 
 struct DescW {
   uint32_t lo, hi, adv;                                   // descriptor words; adv = start-address step per K=16, in 16 B units
@@ -1093,341 +851,18 @@ __device__ __forceinline__ void epi_wait(uint64_t *done, uint32_t &ph) {
   fence_after_sync();
 }
 
-__global__ void __launch_bounds__(kV3Threads, 2)
-field_bwd3_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout, const pn_mlp_grads G) {
-  extern __shared__ __align__(128) uint8_t sm[];
-  __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t ready, done, dx_full, dx_empty;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = uniform_warp_idx();
-  load_all_weights(sm, A);
-  if (warp == 0) tmem_alloc(&tmem_slot, TM_BWD_COLS);
-  if (tid == 0) {
-    mbar_init(&ready, 8); mbar_init(&done, 1); mbar_init(&dx_full, 1); mbar_init(&dx_empty, 128);
-    mbar_fence_init();
-  }
-  fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const int64_t n_tiles = (A.in.n_points + kTcTile - 1) / kTcTile;
-  const int C = A.C;
-
-  if (warp == 12) {
-    // ---------------- MMA role ----------------
-    const bool lead = elect_one();
-    uint32_t pr = 0, n = 0;
-    bool first = true;
-    TLog T = {nullptr, 0, F.tlog_cap};
-    if (F.tlog && blockIdx.x == 0 && lead) T.p = F.tlog + 2 * F.tlog_cap;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      T.mark();
-      // next tile's inputs -> L2 (saved feature tile 8 KB, cotangent rows, positions, keep flags)
-      const int64_t nt = tile + gridDim.x;
-      if (lead && nt < n_tiles) {
-        const int64_t nb = nt * kTcTile;
-        const int64_t rows = (A.in.n_points - nb) < kTcTile ? (A.in.n_points - nb) : kTcTile;
-        prefetch_l2(F.featb + nt * 512, 8192);
-        const uint32_t db = (uint32_t)(rows * C * 4) & ~15u, pb = (uint32_t)(rows * 12) & ~15u;
-        if (db && (((uintptr_t)(dout + nb * C)) & 15) == 0) prefetch_l2(dout + nb * C, db);
-        if (pb && (((uintptr_t)(F.pts + nb * 3)) & 15) == 0) prefetch_l2(F.pts + nb * 3, pb);
-      }
-#define PN_MMA_ROUND(...)                                         \
-  do {                                                            \
-    mbar_wait(&ready, pr); pr ^= 1; fence_after_sync();           \
-    T.mark();                                                     \
-    if (lead) { __VA_ARGS__; mma_commit(&done); }                 \
-    T.mark();                                                     \
-    __syncwarp();                                                 \
-  } while (0)
-      // R1 (D1 still holds the previous tile's dX until the scatter warps have taken it)
-      mbar_wait(&ready, pr); pr ^= 1;
-      if (n > 0) mbar_wait(&dx_empty, (n - 1) & 1);
-      fence_after_sync();
-      T.mark();
-      if (lead) {
-        issue3(tmem + TM_D1, k_major(sm + TS::A0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
-        mma_commit(&done);
-      }
-      T.mark();
-      __syncwarp();
-      PN_MMA_ROUND(issue3(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false));
-      PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::CIN, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
-                   if (A.normals) issue3(tmem + TM_DN, k_major(sm + TS::CIN, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false));
-      PN_MMA_ROUND(issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), k_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 0), 4, false);
-                   if (A.normals) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false));
-      // B1: dC2^T += A2c^T dOut ; dA2 = dOut C2 ; (normals) dNH = dNraw N2
-      PN_MMA_ROUND(issue3(tmem + TM_GC2, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::DOUT, 16), instr_desc(64, 16, 1, 1), 8, !first);
-                   issue3(tmem + TM_D1, k_major(sm + TS::DOUT, 16), mn_major(sm + TS::W_C2, 64), instr_desc(128, 64, 0, 1), 1, false);
-                   if (A.normals) issue3(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false));
-      // B2: dC1 += dA2pre^T A1c ; dA1 = dA2pre C1
-      PN_MMA_ROUND(issue3(tmem + TM_GC1, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::A1C, 64), instr_desc(64, 64, 1, 1), 8, !first);
-                   issue3(tmem + TM_D1, k_major(sm + TS::A2C, 64), mn_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 1), 4, false));
-      // B3: dC0 += dA1pre^T CIN ; dCIN = dA1pre C0 ; (normals) dgeo_n = dNHpre N0
-      PN_MMA_ROUND(issue3(tmem + TM_GC0, mn_major(sm + TS::A1C, 64), mn_major(sm + TS::CIN, 32), instr_desc(64, 32, 1, 1), 8, !first);
-                   issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), mn_major(sm + TS::W_C0, 32), instr_desc(128, 32, 0, 1), 4, false);
-                   if (A.normals) issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false));
-      // B4: dS1^T += H1^T dH2 ; dH1 = dH2 S1
-      PN_MMA_ROUND(issue3(tmem + TM_GS1, mn_major(sm + TS::A1, 64), mn_major(sm + TS::DH2, 16), instr_desc(64, 16, 1, 1), 8, !first);
-                   issue3(tmem + TM_D1, k_major(sm + TS::DH2, 16), mn_major(sm + TS::W_S1, 64), instr_desc(128, 64, 0, 1), 1, false));
-      // B5: dS0 += dH1pre^T X ; dX = dH1pre S0 -> also the scatter warps' go-ahead
-      PN_MMA_ROUND(issue3(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
-                   issue3(tmem + TM_D1, k_major(sm + TS::A1, 64), mn_major(sm + TS::W_S0, 32), instr_desc(128, 32, 0, 1), 4, false);
-                   mma_commit(&dx_full));
-#undef PN_MMA_ROUND
-      first = false;
-    }
-    __syncthreads();
-    return;
-  }
-
-  if (warp >= 8) {
-    // ---------------- scatter role ----------------
-    setmaxnreg_dec<kV3AuxRegs>();
-    uint32_t phs = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t pt = tile * kTcTile + (warp - 8) * 32 + lane;
-      const bool valid = pt < A.in.n_points;
-      float xv[3] = {0.f, 0.f, 0.f};
-      if (valid) { xv[0] = __ldg(F.pts + 3 * pt); xv[1] = __ldg(F.pts + 3 * pt + 1); xv[2] = __ldg(F.pts + 3 * pt + 2); }
-      float g[32];
-      mbar_wait(&dx_full, phs); phs ^= 1; fence_after_sync();
-      tmem_ld16(lane_addr + TM_D1, g);
-      tmem_ld16(lane_addr + TM_D1 + 16, g + 16);
-      tmem_ld_wait();
-      fence_before_sync();
-      mbar_arrive(&dx_empty);
-      bool any = false;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) any = any || (g[j] != 0.f);
-      if (!__any_sync(0xffffffffu, valid && any) || (F.debug & 1)) continue;     // 32 samples without a gradient (empty space)
-#pragma unroll 1
-      for (int l = 0; l < F.G.n_levels; ++l)
-        scatter_level<false>(F.G, F.D.t[l], l, xv, valid ? g[2 * l] : 0.f, valid ? g[2 * l + 1] : 0.f, lane);
-    }
-    __syncthreads();
-    return;
-  }
-
-  // ---------------- epilogue role ----------------
-  setmaxnreg_inc<kV3EpiRegs>();
-  const int p = tid & 127, half = tid >> 7;
-  uint32_t ph = 0;
-  float q[8];
-  const float *qrow = nullptr;
-  if (A.in.act_q) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
-    if (q[5] != 0.f) qrow = q;
-  }
-  float g_n2 = 0.f, g_n0[4] = {0.f, 0.f, 0.f, 0.f};
-  bool first = true;
-  TLog T = {nullptr, 0, F.tlog_cap};
-  if (F.tlog && blockIdx.x == 0 && (tid == 0 || tid == 160)) T.p = F.tlog + (tid ? F.tlog_cap : 0);
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t base = tile * kTcTile;
-    const bool valid = base + p < A.in.n_points;
-    T.mark();
-    // the previous tile's B5 (reader of A0 / A1) was waited for at the end of the previous iteration
-    tc_load_inputs<SRC_TILE>(sm, A, &F, tile, base, p, half, valid);
-    float d_o[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (valid) {
-      if (C == 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(dout + (base + p) * 4));
-        d_o[0] = v.x; d_o[1] = v.y; d_o[2] = v.z; d_o[3] = v.w;
-        if (A.in.keep && A.in.keep[base + p] == 0) d_o[3] = 0.f;                  // run_nerf.py:66
-      } else {
-#pragma unroll
-        for (int c = 0; c < 7; ++c) d_o[c] = __ldg(dout + (base + p) * 7 + c);
-        if (A.in.keep && A.in.keep[base + p] == 0) d_o[6] = 0.f;
-      }
-    }
-    T.mark();
-    epi_arrive(&ready, lane);
-    // E1: H1 = relu(D1) -> A1
-    epi_wait(&done, ph);
-    T.mark();
-    const uint32_t h1_mask = epi_hidden32(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
-    T.mark();
-    epi_arrive(&ready, lane);
-    // E2: [sigma, geo] -> CIN[16..32)
-    epi_wait(&done, ph);
-    T.mark();
-    if (half == 0) {
-      float v[17];
-      tmem_ld16(lane_addr + TM_D2, v);
-      tmem_ld_wait();
-      v[16] = 0.f;
-      st_chunk(sm + TS::CIN, chunk_off(p, 2, 4), v + 1);
-      st_chunk(sm + TS::CIN, chunk_off(p, 3, 4), v + 9);
-    }
-    T.mark();
-    epi_arrive(&ready, lane);
-    // E3: colour hidden 1 -> A1C ; (normals) NH
-    epi_wait(&done, ph);
-    T.mark();
-    epi_hidden32(lane_addr + TM_D1, sm + TS::A1C, p, half, nullptr);
-    if (A.normals) {
-      const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + half * 16;
-      float v[16];
-      tmem_ld16(lane_addr + TM_DN + half * 16, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + bias[j], 0.f);
-      st_chunk(sm + TS::NH, chunk_off(p, half * 2, 4), v);
-      st_chunk(sm + TS::NH, chunk_off(p, half * 2 + 1, 4), v + 8);
-    }
-    T.mark();
-    epi_arrive(&ready, lane);
-    // E4: colour hidden 2 -> A2C ; raw normal ; B0: cotangent tiles
-    epi_wait(&done, ph);
-    T.mark();
-    float nraw[3] = {0.f, 0.f, 0.f};
-    if (A.normals && half == 0) {
-      const float *bias = reinterpret_cast<const float *>(sm + TS::BIAS) + 32;
-      float v[16];
-      tmem_ld16(lane_addr + TM_D2, v);
-      tmem_ld_wait();
-      nraw[0] = v[0] + bias[0]; nraw[1] = v[1] + bias[1]; nraw[2] = v[2] + bias[2];
-    }
-    epi_hidden32(lane_addr + TM_D1, sm + TS::A2C, p, half, nullptr);
-    if (half == 0) {
-      float v[8] = {d_o[0], d_o[1], d_o[2], 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      st_chunk(sm + TS::DOUT, chunk_off(p, 0, 2), v);
-      st_chunk(sm + TS::DOUT, chunk_off(p, 1, 2), z);
-      if (A.normals) {
-        const float nn = sqrtf(nraw[0] * nraw[0] + nraw[1] * nraw[1] + nraw[2] * nraw[2]);
-        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (nn > 1e-12f) {
-          const float m0 = nraw[0] / nn, m1 = nraw[1] / nn, m2 = nraw[2] / nn;
-          const float dot = m0 * d_o[4] + m1 * d_o[5] + m2 * d_o[6];
-          r[0] = (d_o[4] - m0 * dot) / nn; r[1] = (d_o[5] - m1 * dot) / nn; r[2] = (d_o[6] - m2 * dot) / nn;
-        } else {
-          r[0] = d_o[4] / 1e-12f; r[1] = d_o[5] / 1e-12f; r[2] = d_o[6] / 1e-12f;
-        }
-        st_chunk(sm + TS::DNR, chunk_off(p, 0, 2), r);
-        st_chunk(sm + TS::DNR, chunk_off(p, 1, 2), z);
-      }
-    }
-    T.mark();
-    epi_arrive(&ready, lane);
-    // normal head weight gradients on the CUDA cores (611 numbers): every row of NH / DNR must be written first
-    if (A.normals) {
-      mlp_sync();
-      if (tid < 99) {
-        const int j = tid < 96 ? tid >> 5 : tid - 96, k = tid & 31;
-        float s = 0.f;
-        for (int r = 0; r < kTcTile; ++r)
-          s += tile_elem(sm + TS::DNR, r, j, 2) * (tid < 96 ? tile_elem(sm + TS::NH, r, k, 4) : 1.f);
-        g_n2 += s;
-      }
-    }
-    // E(B1): dA2pre -> A2C (in place, masked) ; (normals) dNHpre -> NH
-    epi_wait(&done, ph);
-    T.mark();
-    if (A.normals) mlp_sync();                     // all NH reads above are done
-    epi_grad32(lane_addr + TM_D1, sm + TS::A2C, p, half, false, 0);
-    if (A.normals) {
-      float v[16];
-      tmem_ld16(lane_addr + TM_DN + half * 16, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float a[8];
-        ld_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), a);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * c + j] = a[j] > 0.f ? v[8 * c + j] : 0.f;
-        st_chunk(sm + TS::NH, chunk_off(p, half * 2 + c, 4), v + 8 * c);
-      }
-    }
-    T.mark();
-    epi_arrive(&ready, lane);
-    if (A.normals) {
-      mlp_sync();                                  // dNHpre rows of every thread are written
-      if (tid < 128) {                             // dN0w[j][k] (k < 15) and dN0b[j] (k == 15): 4 outputs per thread
-        const int j = tid >> 2, k0 = (tid & 3) * 4;
-        for (int r = 0; r < kTcTile; ++r) {
-          const float d = tile_elem(sm + TS::NH, r, j, 4);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            g_n0[i] += d * ((k0 + i) < 15 ? tile_elem(sm + TS::CIN, r, 16 + k0 + i, 4) : 1.f);
-        }
-      }
-    }
-    // E(B2): dA1pre -> A1C
-    epi_wait(&done, ph);
-    T.mark();
-    epi_grad32(lane_addr + TM_D1, sm + TS::A1C, p, half, false, 0);
-    T.mark();
-    epi_arrive(&ready, lane);
-    // E(B3): [dsigma, dgeo] -> DH2
-    epi_wait(&done, ph);
-    T.mark();
-    if (half == 1) {
-      float g[17];
-      tmem_ld16(lane_addr + TM_D1 + 16, g + 1);        // dCIN[16..32) = dgeo[0..15) + pad
-      tmem_ld_wait();
-      if (A.normals) {
-        float v[16];
-        tmem_ld16(lane_addr + TM_D2, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 15; ++j) g[1 + j] += v[j];
-      }
-      g[0] = d_o[3];                                   // dsigma (keep mask applied above when C == 4)
-      st_chunk(sm + TS::DH2, chunk_off(p, 0, 2), g);
-      st_chunk(sm + TS::DH2, chunk_off(p, 1, 2), g + 8);
-    }
-    T.mark();
-    epi_arrive(&ready, lane);
-    // E(B4): dH1pre -> A1
-    epi_wait(&done, ph);
-    T.mark();
-    epi_grad32(lane_addr + TM_D1, sm + TS::A1, p, half, true, h1_mask);
-    T.mark();
-    epi_arrive(&ready, lane);
-    // B5 reads A1 and A0: wait for it before the next tile's inputs overwrite them
-    epi_wait(&done, ph);
-    T.mark();
-    first = false;
-  }
-  // flush the weight gradients (every MMA has completed: the last commit was waited on)
-  if (!first && warp < 4) {
-    const bool owner = lane < 16;
-    const int row = warp * 16 + lane;
-    flush_acc(lane_addr + TM_GC1, 64, owner, row, G.c1, 64, 64, 64, false);
-    flush_acc(lane_addr + TM_GS0, 32, owner, row, G.s0, 32, 64, 32, false);
-    flush_acc(lane_addr + TM_GC0, 32, owner, row, G.c0, 31, 64, 31, false);
-    flush_acc(lane_addr + TM_GS1, 16, owner, row, G.s1, 64, 64, 16, true);
-    flush_acc(lane_addr + TM_GC2, 16, owner, row, G.c2, 64, 64, 3, true);
-  }
-  if (!first && A.normals) {
-    if (tid < 96) { if (G.n2w) atomicAdd(G.n2w + (tid >> 5) * 32 + (tid & 31), g_n2); }
-    else if (tid < 99) { if (G.n2b) atomicAdd(G.n2b + (tid - 96), g_n2); }
-    if (tid < 128) {
-      const int j = tid >> 2, k0 = (tid & 3) * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (k0 + i < 15) { if (G.n0w) atomicAdd(G.n0w + j * 15 + k0 + i, g_n0[i]); }
-        else if (G.n0b) atomicAdd(G.n0b + j, g_n0[i]);
-      }
-    }
-  }
-  fence_before_sync(); __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TM_BWD_COLS);
-}
-
 
 // ------------------------------------------------------------------------------------------------------
-// Fused backward, fourth structure (pn_field_bwd_bf16 default): the v3 roles with the scatter DECOUPLED from the
+// Fused backward (pn_field_bwd_bf16 default): three roles per CTA, 2 CTAs per SM, with the scatter DECOUPLED from the
 // round chain through a small ring in global memory (L2-resident: kRingSlots x 16 KB per CTA).
 //   warps 0-7   epilogue; after B5 each thread copies its half row of dX (TMEM, fp32) into the CTA's ring slot
-//   warp  8     MMA issuer (as v3)
+//   warp  8     MMA issuer
 //   warps 9-15  scatter: 7 warps take (tile, 4 levels) items round-robin from the ring — any warp can take any item
 //               (the TMEM lane-quarter rule no longer applies), and they may lag the chain by kRingSlots tiles; a lane
 //               walks 4 consecutive samples serially per level (scatter_segment: run aggregation without shuffles).
 // Why: with the training step's own gradients nearly every warp of 32 samples has some non-zero rows, so the scatter
 // costs its full ~230 instructions per level per warp; 4 scatter warps tied to the chain by a one-tile TMEM hand-off
-// (v3) took ~30 k cycles per tile against ~13 k for the chain.  What the scatter needs is issue slots from many warps
+// (an earlier structure of this round) took ~30 k cycles per tile against ~13 k for the chain.  What the scatter needs is issue slots from many warps
 // (the standalone scatter kernel reaches 71 % issue utilisation with 32 warps/SM), not a place in the chain.
 // ------------------------------------------------------------------------------------------------------
 #ifndef PN_V4_SCATTER_WARPS
@@ -1870,27 +1305,6 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
     attr_set[dev] = true;
   }
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
-  // fused field forward: PN_FIELD_FWD=ws selects the warp-specialised kernel (PN_FWD_GW=4|8 gather warps)
-  static int ws_gw = -1;
-  if (ws_gw < 0) {
-    const char *e = getenv("PN_FIELD_FWD"), *g = getenv("PN_FWD_GW");
-    ws_gw = (e && e[0] == 'w') ? ((g && atoi(g) == 4) ? 4 : 8) : 0;      // default: single-role kernel (measured faster)
-  }
-  if (fused && !packed && ws_gw) {
-    static bool ws_attr[64] = {false};
-    if (dev >= 0 && dev < 64 && !ws_attr[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(field_fwd_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW::END);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(field_fwd_ws_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW::END);
-      PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(field_fwd_ws): %s", cudaGetErrorString(e));
-      ws_attr[dev] = true;
-    }
-    const int64_t cap2 = (int64_t)sm_count() * 2;
-    const int blocks2 = (int)(tiles < cap2 ? tiles : cap2);
-    if (ws_gw == 4) field_fwd_ws_kernel<4><<<blocks2, kTcThreads + 128, FW::END, st>>>(A, F, out);
-    else field_fwd_ws_kernel<8><<<blocks2, kTcThreads + 256, FW::END, st>>>(A, F, out);
-    count_launch();
-    return check_launch("field_fwd_ws_kernel");
-  }
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int blocks = (int)(tiles < cap ? tiles : cap);
   if (packed) mlp_tc_fwd_kernel<3, SRC_PACKED><<<blocks, kTcThreads, smem, st>>>(A, F, out);
@@ -1902,13 +1316,13 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
   return check_launch("mlp_tc_fwd_kernel");
 }
 
-// Which fused backward runs (PN_FIELD_BWD): "v4" three roles + ring-decoupled scatter (default), "v3" three roles with
-// the TMEM hand-off, "ws" two-role kernel, "v1" single-role kernel.
+// Which fused backward runs (PN_FIELD_BWD): the three-role kernel with the ring-decoupled scatter (default) or "v1", the
+// single-role kernel it replaced — kept as the instrumented baseline (clock64 timeline) the design was derived from.
 static int bwd_variant() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("PN_FIELD_BWD");
-    v = !e ? 3 : ((e[0] == 'v' && e[1] == '1') ? 0 : (e[0] == 'w' ? 1 : ((e[0] == 'v' && e[1] == '3') ? 2 : 3)));
+    v = (e && e[0] == 'v' && e[1] == '1') ? 0 : 3;
   }
   return v;
 }
@@ -1923,10 +1337,8 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_F32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1937,7 +1349,7 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
   const int64_t tiles = ceil_div(A.in.n_points, kTcTile);
   const int64_t cap = (int64_t)sm_count() * 2;          // 2 CTAs/SM: 2 x 256 TMEM columns, 2 x 107 KB smem
   const int blocks = (int)(tiles < cap ? tiles : cap);
-  if (fused && bwd_variant() >= 2) PN_REQUIRE(A.C == 7 || ((uintptr_t)dout & 15) == 0, PN_EINVAL, "dout must be 16-byte aligned");
+  if (fused && bwd_variant() == 3) PN_REQUIRE(A.C == 7 || ((uintptr_t)dout & 15) == 0, PN_EINVAL, "dout must be 16-byte aligned");
   if (fused && bwd_variant() == 3) {
     PN_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= field_bwd_workspace_bytes(), PN_EINVAL,
                "pn_field_bwd_bf16 needs a 16-byte aligned workspace of pn_field_bwd_workspace_bytes() = %lld bytes (got %lld)",
@@ -1953,14 +1365,10 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
     else if (A.normals) field_bwd4_kernel<true, false><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
     else if (seg) field_bwd4_kernel<false, true><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
     else field_bwd4_kernel<false, false><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
-  } else if (fused && bwd_variant() == 2) {
-    field_bwd3_kernel<<<blocks, kV3Threads, smem, st>>>(A, F, dout, dw);
-  } else if (fused && bwd_variant() == 1)
-    mlp_tc_bwd_kernel<SRC_TILE, true><<<blocks, kWsThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
-  else if (fused)
-    mlp_tc_bwd_kernel<SRC_TILE, false><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
+  } else if (fused)
+    mlp_tc_bwd_kernel<SRC_TILE><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
   else
-    mlp_tc_bwd_kernel<SRC_F32, false><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
+    mlp_tc_bwd_kernel<SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
   count_launch();
   return check_launch("mlp_tc_bwd_kernel");
 }

@@ -1,7 +1,8 @@
 """Kernel-only timing of the two fused field kernels of the bf16 training step (pn_field_fwd_bf16 / pn_field_bwd_bf16)
 on the step's own point sets: 65536 rays x 192 samples (fine pass) and x 64 (coarse pass), ray-ordered, T = 2^19 (or
 --log2T 22).  CUDA events around back-to-back launches, 3 warm-up + 10 timed.  The kernel variant is chosen by the
-environment (read once per process): PN_FIELD_FWD=v1|ws, PN_FWD_GW=4|8, PN_FIELD_BWD=v1|ws.
+environment (read once per process): PN_FIELD_BWD=v1 (single-role kernel) or unset (three-role kernel); PN_DEBUG_FLAGS=1
+skips the scatter work, 2 the gather work (measurement only).
 
     python scripts/bench_field_kernels.py [--log2T 19] [--normals]            # one JSON line
     python scripts/bench_field_kernels.py --sweep                             # every variant, one subprocess each
@@ -16,9 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 # (PN_FIELD_FWD, PN_FWD_GW, PN_FIELD_BWD, PN_DEBUG_FLAGS, extra args)
-VARIANTS = [("v1", "8", "v1", "0", []), ("v1", "8", "v3", "0", []), ("v1", "8", "v4", "0", []),
-            ("v1", "8", "v1", "0", ["--density", "0.1"]), ("v1", "8", "v3", "0", ["--density", "0.1"]),
-            ("v1", "8", "v4", "0", ["--density", "0.1"]), ("v1", "8", "v4", "1", [])]
+VARIANTS = [("v1", "8", "v1", "0", []), ("v1", "8", "v4", "0", []),
+            ("v1", "8", "v1", "0", ["--density", "0.1"]), ("v1", "8", "v4", "0", ["--density", "0.1"]),
+            ("v1", "8", "v4", "1", [])]
 
 
 def sweep(extra):

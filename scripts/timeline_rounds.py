@@ -1,13 +1,13 @@
 """Per-round latency table of the fused backward kernel (pn_field_bwd_bf16) from the clock64 marks that
 pn_debug_timeline installs: where, inside one 128-point tile, do the cycles go?
 
-    PN_FIELD_BWD=v1|ws|v3 [PN_DEBUG_FLAGS=1] python scripts/timeline_rounds.py [--density 0.1]
+    PN_FIELD_BWD=v1 [PN_DEBUG_FLAGS=1] python scripts/timeline_rounds.py [--density 0.1]
 
-v1 / ws marks per tile (thread 0 = MMA issuer, thread 160 = plain epilogue thread), see mlp_tc.cu:
+Instrumented kernel: the single-role fused backward (mlp_tc_bwd_kernel<SRC_TILE>, PN_FIELD_BWD=v1).  Marks per tile
+(thread 0 = MMA issuer, thread 160 = plain epilogue thread), see mlp_tc.cu:
   0 tile start | 1 inputs loaded | per forward round R1..R4: issue-start, issue-end, mma-done, epilogue-done |
   18 cotangent tiles written | per backward round B1..B4: the same four | B5: issue-start, issue-end, mma-done | 38 tile end
-v3 marks: epilogue threads 0 tile start | 1 inputs loaded | per round: mma-done, epilogue-done (B5: mma-done only);
-  MMA warp 0 tile start | per round: operands-ready, issued.
+The tables this produced in round 2 (profiles/r02_timeline_*.txt) are what the three-role kernel was designed from.
 """
 import argparse
 import ctypes
@@ -64,8 +64,9 @@ def main():
     vd = rays[1] / rays[1].norm(dim=-1, keepdim=True)
     z = torch.sort(2.0 + 4.0 * torch.rand(65536, 192, device=dev), -1)[0]
     pts = ops.make_points(rays[0], rays[1], z)
-    variant = os.environ.get("PN_FIELD_BWD", "v3")
-    v3 = not (variant.startswith("v1") or variant.startswith("w"))
+    if not os.environ.get("PN_FIELD_BWD", "").startswith("v1"):
+        sys.exit("set PN_FIELD_BWD=v1: only the single-role kernel carries the clock64 marks")
+    v3 = False
     tiles = 14
     cap = 40 * tiles
     buf = torch.zeros(3, cap, dtype=torch.int64, device=dev)
