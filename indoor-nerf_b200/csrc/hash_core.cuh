@@ -132,14 +132,14 @@ PN_HD uint32_t corner_index(const HashGridDev &G, const Cell &c, int corner) {
 // only in x (prime 1): when the voxel's x index is even their rows are h and h ^ 1, i.e. ONE aligned 16-byte entry pair,
 // fetched with one load instead of two.  A scattered gather costs the LSU one wavefront per distinct line it touches
 // whatever the access width, and a gather that misses the L2 moves a 32-byte DRAM sector per row: pairing removes a
-// quarter of both.  Only used by the stand-alone encoder (ALLOW_PAIR) when the table set does not fit the L2
-// (G.pair_gather): inside the fused forward the two-way divergence costs more than it saves at either table size
+// quarter of both.  Only used by the stand-alone encoder (PAIR, a kernel template parameter the launcher sets from
+// G.pair_gather) when the table set does not fit the L2: inside the fused forward the two-way divergence costs more than it saves at either table size
 // (T = 2^22, fine pass: 3.35 -> 4.32 ms).  Values are bit-identical.
 #if defined(__CUDACC__)
-template <bool ALLOW_PAIR>
+template <bool PAIR>
 __device__ __forceinline__ void gather8(const HashGridDev &G, const float2 *__restrict__ tab, const Cell &c, float e0[8],
                                         float e1[8]) {
-  if (ALLOW_PAIR && G.pair_gather && (c.hx0 & 1u) == 0u) {
+  if (PAIR && (c.hx0 & 1u) == 0u) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t i0 = corner_index(G, c, k);                        // dx = 0 row; the dx = 1 row is i0 ^ 1

@@ -25,7 +25,7 @@ __device__ __forceinline__ void load_point(const float *__restrict__ x, int64_t 
   xv[2] = __ldg(x + 3 * p + 2);
 }
 
-template <bool QUANT>
+template <bool QUANT, bool PAIR>
 __global__ void __launch_bounds__(kHashThreads)
 hash_fwd_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ TablePtrs T, const float *__restrict__ qparams,
                 const float *__restrict__ x, int64_t P, float *__restrict__ feat,
@@ -45,7 +45,7 @@ hash_fwd_kernel(const __grid_constant__ HashGridDev G, const __grid_constant__ T
       Cell c;
       point_cell(G, l, xv, c);
       float e0[8], e1[8];
-      gather8<true>(G, T.t[l], c, e0, e1);
+      gather8<PAIR>(G, T.t[l], c, e0, e1);
       if (QUANT) {
         const float *q = qparams + l * PN_QROW;
         if (q[5] != 0.f) {
@@ -283,10 +283,14 @@ extern "C" int pn_hash_encode_fwd(const pn_hash_grid *grid, const float *const *
     PN_REQUIRE(tables[l] != nullptr && ((uintptr_t)tables[l] & 15) == 0, PN_EINVAL,
                "tables[%d] is NULL or not 16-byte aligned (x-adjacent corner rows are fetched as one 16-byte pair)", l);
   const int blocks = hash_blocks(n_points, kHashThreads, 16);
-  if (qparams)
-    hash_fwd_kernel<true><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, qparams, x, n_points, feat, keep);
+  if (qparams && G.pair_gather)
+    hash_fwd_kernel<true, true><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, qparams, x, n_points, feat, keep);
+  else if (qparams)
+    hash_fwd_kernel<true, false><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, qparams, x, n_points, feat, keep);
+  else if (G.pair_gather)
+    hash_fwd_kernel<false, true><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, nullptr, x, n_points, feat, keep);
   else
-    hash_fwd_kernel<false><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, nullptr, x, n_points, feat, keep);
+    hash_fwd_kernel<false, false><<<blocks, kHashThreads, 0, as_stream(stream)>>>(G, T, nullptr, x, n_points, feat, keep);
   count_launch();
   return check_launch("hash_fwd_kernel");
 }
