@@ -204,6 +204,39 @@ __device__ __forceinline__ void issue(uint32_t d, const Opnd &a, const Opnd &b, 
             (accumulate || k > 0) ? 1u : 0u);
 }
 
+struct DescW {
+  uint32_t lo, hi, adv;                                   // descriptor words; adv = start-address step per K=16, in 16 B units
+};
+__device__ __forceinline__ DescW desc_words(const Opnd &o) {
+  DescW d;
+  d.lo = ((o.addr & 0x3FFFFu) >> 4) | (((o.lbo >> 4) & 0x3FFFu) << 16);
+  d.hi = ((o.sbo >> 4) & 0x3FFFu) | (1u << 14);
+  d.adv = o.adv >> 4;
+  return d;
+}
+__device__ __forceinline__ void issue3(uint32_t d, const Opnd &a, const Opnd &b, uint32_t idesc, int ksteps, bool accumulate) {
+  const DescW da = desc_words(a), db = desc_words(b);
+#pragma unroll
+  for (int k = 0; k < ksteps; ++k)
+    mma_f16(d, ((uint64_t)da.hi << 32) | (uint64_t)(da.lo + k * da.adv), ((uint64_t)db.hi << 32) | (uint64_t)(db.lo + k * db.adv),
+            idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+
+// Who issues the MMAs in the single-role kernels: warp 0 enters the issue block as a whole (a warp-uniform branch, so the
+// descriptor arithmetic stays on the uniform datapath — from a divergent `threadIdx.x == 0` branch each tcgen05.mma
+// cost ~80 cycles of R2UR traffic, clock64 timeline of round 2) and one elected lane issues.
+struct Issuer {
+  bool warp0, lead;
+};
+__device__ __forceinline__ Issuer make_issuer() {
+  Issuer iw;
+  iw.warp0 = uniform_warp_idx() == 0;
+  iw.lead = elect_one() && iw.warp0;
+  return iw;
+}
+#define PN_ISSUE_BEGIN(iw) if ((iw).warp0) { fence_after_sync(); if ((iw).lead) {
+#define PN_ISSUE_END(iw, bar) mma_commit(bar); } __syncwarp(); }
+
 // Thread mapping: 256 threads per 128-point tile.  Thread (p = tid & 127, half = tid >> 7) owns row p and
 // half of the columns of every epilogue; warps w and w+4 share TMEM lane quarter w (a warp may only touch
 // lanes 32*(warp%4) .. +31), so both halves read the same accumulator rows, different columns.
@@ -353,23 +386,17 @@ __device__ __forceinline__ void mlp_sync() { named_bar_sync<1, 256>(); }
 template <bool BWD>
 __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_t tmem, uint32_t lane_addr, uint64_t *bar,
                                            uint32_t &ph, int p, int half, const float *qrow, float &sigma,
-                                           float nraw[3], uint32_t &h1_mask, uint64_t *r1_gate = nullptr,
-                                           uint32_t r1_gate_parity = 0, int a0_off = TS::A0, int cin_off = TS::CIN,
-                                           uint64_t *r3_release = nullptr, TLog *tl = nullptr) {
+                                           float nraw[3], uint32_t &h1_mask, const Issuer &iw, TLog *tl = nullptr) {
   TLog none = {nullptr, 0, 0};
   TLog &T = tl ? *tl : none;
-  const bool t0 = threadIdx.x == 0;
   uint8_t *a1c = BWD ? sm + TS::A1C : sm + TS::A1;
   uint8_t *a2c = BWD ? sm + TS::A2C : sm + TS::A1;
-  uint8_t *a0 = sm + a0_off, *cin = sm + cin_off;      // double-buffered by the warp-specialised forward
+  uint8_t *a0 = sm + TS::A0, *cin = sm + TS::CIN;
   // R1: H1 = relu(X S0^T)
   T.mark();
-  if (t0) {
-    if (r1_gate) mbar_wait(r1_gate, r1_gate_parity);   // D1 still holds the previous tile's dX until it is taken
-    fence_after_sync();
-    issue(tmem + TM_D1, k_major(a0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
-    mma_commit(bar);
-  }
+  PN_ISSUE_BEGIN(iw)
+    issue3(tmem + TM_D1, k_major(a0, 32), k_major(sm + TS::W_S0, 32), instr_desc(128, 64, 0, 0), 2, false);
+  PN_ISSUE_END(iw, bar)
   T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
   T.mark();
@@ -378,11 +405,9 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
   PN_ROUND_SYNC();
   // R2: [sigma, geo] = H1 S1^T
   T.mark();
-  if (t0) {
-    fence_after_sync();
-    issue(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false);
-    mma_commit(bar);
-  }
+  PN_ISSUE_BEGIN(iw)
+    issue3(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_S1, 64), instr_desc(128, 16, 0, 0), 4, false);
+  PN_ISSUE_END(iw, bar)
   T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
   T.mark();
@@ -399,14 +424,11 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
   PN_ROUND_SYNC();
   // R3: A1c = relu(CIN C0^T);  NH = relu(geo N0^T + b)
   T.mark();
-  if (t0) {
-    fence_after_sync();
-    issue(tmem + TM_D1, k_major(cin, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
+  PN_ISSUE_BEGIN(iw)
+    issue3(tmem + TM_D1, k_major(cin, 32), k_major(sm + TS::W_C0, 32), instr_desc(128, 64, 0, 0), 2, false);
     if (A.normals)
-      issue(tmem + TM_DN, k_major(cin, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false);
-    mma_commit(bar);
-    if (r3_release) mma_commit(r3_release);            // last reader of this tile's A0 / CIN buffer
-  }
+      issue3(tmem + TM_DN, k_major(cin, 32, 16), k_major(sm + TS::W_N0, 16), instr_desc(128, 32, 0, 0), 1, false);
+  PN_ISSUE_END(iw, bar)
   T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
   T.mark();
@@ -425,13 +447,11 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
   PN_ROUND_SYNC();
   // R4: A2c = relu(A1c C1^T);  raw normal = NH N2^T + b
   T.mark();
-  if (t0) {
-    fence_after_sync();
-    issue(tmem + TM_D1, k_major(a1c, 64), k_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 0), 4, false);
+  PN_ISSUE_BEGIN(iw)
+    issue3(tmem + TM_D1, k_major(a1c, 64), k_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 0), 4, false);
     if (A.normals)
-      issue(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false);
-    mma_commit(bar);
-  }
+      issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), k_major(sm + TS::W_N2, 32), instr_desc(128, 16, 0, 0), 2, false);
+  PN_ISSUE_END(iw, bar)
   T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
   T.mark();
@@ -460,6 +480,7 @@ mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__
   fence_async_smem(); fence_before_sync(); __syncthreads(); fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const Issuer iw = make_issuer();
   uint32_t ph = 0;
   float q[8];
   const float *qrow = nullptr;
@@ -472,17 +493,22 @@ mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kTcTile;
     const bool valid = base + p < A.in.n_points;
+    // the next tile's positions -> L2 while this one runs (SRC_HASH / SRC_PACKED read them right at the start of a tile)
+    if ((SRC == SRC_HASH || SRC == SRC_PACKED) && iw.lead && tile + gridDim.x < n_tiles) {
+      const int64_t nb = (tile + gridDim.x) * kTcTile;
+      const int64_t rows = (A.in.n_points - nb) < kTcTile ? (A.in.n_points - nb) : kTcTile;
+      const uint32_t pb = (uint32_t)(rows * 12) & ~15u;
+      if (pb && (((uintptr_t)(F.pts + nb * 3)) & 15) == 0) prefetch_l2(F.pts + nb * 3, pb);
+    }
     tc_load_inputs<SRC>(sm, A, &F, tile, base, p, half, valid);
     PN_ROUND_SYNC();
     float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
     uint32_t m;
-    tc_forward<false>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, m);
+    tc_forward<false>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, m, iw);
     // R5: rgb = A2c C2^T
-    if (tid == 0) {
-      fence_after_sync();
-      issue(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_C2, 64), instr_desc(128, 16, 0, 0), 4, false);
-      mma_commit(&bar);
-    }
+    PN_ISSUE_BEGIN(iw)
+      issue3(tmem + TM_D2, k_major(sm + TS::A1, 64), k_major(sm + TS::W_C2, 64), instr_desc(128, 16, 0, 0), 4, false);
+    PN_ISSUE_END(iw, &bar)
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
     if (half == 0) {
       float v[16];
@@ -582,7 +608,7 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   }
   // normal-head weight gradients are reduced on the CUDA cores (tiny: 611 numbers), fp32 registers across tiles
   float g_n2 = 0.f, g_n0[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool t0 = tid == 0;
+  const Issuer iw = make_issuer();
   bool first = true;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kTcTile;
@@ -598,8 +624,7 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     PN_ROUND_SYNC();
     float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
     uint32_t h1_mask;
-    tc_forward<true>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, h1_mask, nullptr, 0, TS::A0, TS::CIN,
-                     nullptr, &T);
+    tc_forward<true>(sm, A, tmem, lane_addr, &bar, ph, p, half, qrow, sigma, nraw, h1_mask, iw, &T);
 
     // B0: cotangent tiles (half 0 owns the row-level values)
     if (half == 0) {
@@ -624,14 +649,12 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     PN_ROUND_SYNC();
     // B1: dC2^T += A2c^T dOut ; dA2 = dOut C2 ; (normals) dNH = dNraw N2
     T.mark();
-    if (t0) {
-      fence_after_sync();
-      issue(tmem + TM_GC2, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::DOUT, 16), instr_desc(64, 16, 1, 1), 8, !first);
-      issue(tmem + TM_D1, k_major(sm + TS::DOUT, 16), mn_major(sm + TS::W_C2, 64), instr_desc(128, 64, 0, 1), 1, false);
+    PN_ISSUE_BEGIN(iw)
+      issue3(tmem + TM_GC2, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::DOUT, 16), instr_desc(64, 16, 1, 1), 8, !first);
+      issue3(tmem + TM_D1, k_major(sm + TS::DOUT, 16), mn_major(sm + TS::W_C2, 64), instr_desc(128, 64, 0, 1), 1, false);
       if (A.normals)
-        issue(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false);
-      mma_commit(&bar);
-    }
+        issue3(tmem + TM_DN, k_major(sm + TS::DNR, 16), mn_major(sm + TS::W_N2, 32), instr_desc(128, 32, 0, 1), 1, false);
+    PN_ISSUE_END(iw, &bar)
     if (A.normals && tid < 99) {                   // dN2w[j][k] / dN2b[j] on the CUDA cores (needs NH before E1 overwrites it)
       const int j = tid < 96 ? tid >> 5 : tid - 96, k = tid & 31;
       float s = 0.f;
@@ -661,12 +684,10 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     PN_ROUND_SYNC();
     // B2: dC1 += dA2pre^T A1c ; dA1 = dA2pre C1
     T.mark();
-    if (t0) {
-      fence_after_sync();
-      issue(tmem + TM_GC1, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::A1C, 64), instr_desc(64, 64, 1, 1), 8, !first);
-      issue(tmem + TM_D1, k_major(sm + TS::A2C, 64), mn_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 1), 4, false);
-      mma_commit(&bar);
-    }
+    PN_ISSUE_BEGIN(iw)
+      issue3(tmem + TM_GC1, mn_major(sm + TS::A2C, 64), mn_major(sm + TS::A1C, 64), instr_desc(64, 64, 1, 1), 8, !first);
+      issue3(tmem + TM_D1, k_major(sm + TS::A2C, 64), mn_major(sm + TS::W_C1, 64), instr_desc(128, 64, 0, 1), 4, false);
+    PN_ISSUE_END(iw, &bar)
     if (A.normals && tid < 128) {                  // dN0w[j][k] (k < 15) and dN0b[j] (k == 15): 4 outputs per thread
       const int j = tid >> 2, k0 = (tid & 3) * 4;
       for (int r = 0; r < kTcTile; ++r) {
@@ -684,14 +705,12 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     PN_ROUND_SYNC();
     // B3: dC0 += dA1pre^T CIN ; dCIN = dA1pre C0 ; (normals) dgeo_n = dNHpre N0
     T.mark();
-    if (t0) {
-      fence_after_sync();
-      issue(tmem + TM_GC0, mn_major(sm + TS::A1C, 64), mn_major(sm + TS::CIN, 32), instr_desc(64, 32, 1, 1), 8, !first);
-      issue(tmem + TM_D1, k_major(sm + TS::A1C, 64), mn_major(sm + TS::W_C0, 32), instr_desc(128, 32, 0, 1), 4, false);
+    PN_ISSUE_BEGIN(iw)
+      issue3(tmem + TM_GC0, mn_major(sm + TS::A1C, 64), mn_major(sm + TS::CIN, 32), instr_desc(64, 32, 1, 1), 8, !first);
+      issue3(tmem + TM_D1, k_major(sm + TS::A1C, 64), mn_major(sm + TS::W_C0, 32), instr_desc(128, 32, 0, 1), 4, false);
       if (A.normals)
-        issue(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false);
-      mma_commit(&bar);
-    }
+        issue3(tmem + TM_D2, k_major(sm + TS::NH, 32), mn_major(sm + TS::W_N0, 16), instr_desc(128, 16, 0, 1), 2, false);
+    PN_ISSUE_END(iw, &bar)
     T.mark();
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
     T.mark();
@@ -725,12 +744,10 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     PN_ROUND_SYNC();
     // B4: dS1^T += H1^T dH2 ; dH1 = dH2 S1
     T.mark();
-    if (t0) {
-      fence_after_sync();
-      issue(tmem + TM_GS1, mn_major(sm + TS::A1, 64), mn_major(sm + TS::DH2, 16), instr_desc(64, 16, 1, 1), 8, !first);
-      issue(tmem + TM_D1, k_major(sm + TS::DH2, 16), mn_major(sm + TS::W_S1, 64), instr_desc(128, 64, 0, 1), 1, false);
-      mma_commit(&bar);
-    }
+    PN_ISSUE_BEGIN(iw)
+      issue3(tmem + TM_GS1, mn_major(sm + TS::A1, 64), mn_major(sm + TS::DH2, 16), instr_desc(64, 16, 1, 1), 8, !first);
+      issue3(tmem + TM_D1, k_major(sm + TS::DH2, 16), mn_major(sm + TS::W_S1, 64), instr_desc(128, 64, 0, 1), 1, false);
+    PN_ISSUE_END(iw, &bar)
     T.mark();
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
     T.mark();
@@ -739,12 +756,10 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     PN_ROUND_SYNC();
     // B5: dS0 += dH1pre^T X ; dX = dH1pre S0
     T.mark();
-    if (t0) {
-      fence_after_sync();
-      issue(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
-      issue(tmem + TM_D1, k_major(sm + TS::A1, 64), mn_major(sm + TS::W_S0, 32), instr_desc(128, 32, 0, 1), 4, false);
-      mma_commit(&bar);
-    }
+    PN_ISSUE_BEGIN(iw)
+      issue3(tmem + TM_GS0, mn_major(sm + TS::A1, 64), mn_major(sm + TS::A0, 32), instr_desc(64, 32, 1, 1), 8, !first);
+      issue3(tmem + TM_D1, k_major(sm + TS::A1, 64), mn_major(sm + TS::W_S0, 32), instr_desc(128, 32, 0, 1), 4, false);
+    PN_ISSUE_END(iw, &bar)
     T.mark();
     mbar_wait(&bar, ph); ph ^= 1; fence_after_sync();
     T.mark();
@@ -819,24 +834,6 @@ mlp_tc_bwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
 // (uniform datapath, ~20-40 cycles per MMA), prefetches the next tile's inputs into L2, and the epilogue warps never
 // issue or meet at a CTA barrier: they arrive on `ready` (one elected lane per warp) and go straight to waiting on `done`.
 // ------------------------------------------------------------------------------------------------------
-
-struct DescW {
-  uint32_t lo, hi, adv;                                   // descriptor words; adv = start-address step per K=16, in 16 B units
-};
-__device__ __forceinline__ DescW desc_words(const Opnd &o) {
-  DescW d;
-  d.lo = ((o.addr & 0x3FFFFu) >> 4) | (((o.lbo >> 4) & 0x3FFFu) << 16);
-  d.hi = ((o.sbo >> 4) & 0x3FFFu) | (1u << 14);
-  d.adv = o.adv >> 4;
-  return d;
-}
-__device__ __forceinline__ void issue3(uint32_t d, const Opnd &a, const Opnd &b, uint32_t idesc, int ksteps, bool accumulate) {
-  const DescW da = desc_words(a), db = desc_words(b);
-#pragma unroll
-  for (int k = 0; k < ksteps; ++k)
-    mma_f16(d, ((uint64_t)da.hi << 32) | (uint64_t)(da.lo + k * da.adv), ((uint64_t)db.hi << 32) | (uint64_t)(db.lo + k * db.adv),
-            idesc, (accumulate || k > 0) ? 1u : 0u);
-}
 
 // epilogue warps: this round's operand tiles are written -> one arrival per warp on `ready`
 __device__ __forceinline__ void epi_arrive(uint64_t *ready, int lane) {
