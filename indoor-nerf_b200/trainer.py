@@ -54,7 +54,15 @@ class Trainer:
         loss, img_loss = self.losses(rgb, extras, target_s, depth)
         loss.backward()
         if self.world > 1:
-            parallel.allreduce_gradients(self.embed_fn, self.nets, self.group)
+            from . import ops
+            if ops.KERNEL_EVENTS is not None:                      # bench.py's live timing of the step's one collective
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                parallel.allreduce_gradients(self.embed_fn, self.nets, self.group)
+                e1.record()
+                ops.KERNEL_EVENTS.append(("allreduce_gradients", batch_rays.shape[1], e0, e1))
+            else:
+                parallel.allreduce_gradients(self.embed_fn, self.nets, self.group)
         self.opt.step()
         self.step_idx += 1
         if self.step_idx > 1000:                                   # run_nerf.py:1036-1037
