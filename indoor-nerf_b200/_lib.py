@@ -144,7 +144,14 @@ def call(name, *args):
         raise PocketNerfError("%s failed (%d): %s" % (name, rc, lib().pn_last_error().decode()))
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """The current CUDA stream of the current device as a cudaStream_t.  torch.cuda.current_stream() builds a Stream
+    object per call (~18 us, 26 calls per training step); the raw getter is a plain C call."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -34,9 +34,18 @@ def get_mlp_mode():
     return _MLP_MODE
 
 
+import contextlib
+
+_SAME_DEVICE = contextlib.nullcontext()
+
+
 def _guard(t):
+    """Context that makes t's device current for the launch.  The common case (already current) costs one comparison
+    instead of a torch.cuda.device() enter / exit pair."""
     if not t.is_cuda:
         raise _lib.PocketNerfError("expected a CUDA tensor, got device %s — there is no CPU path" % t.device)
+    if t.device.index == torch.cuda.current_device():
+        return _SAME_DEVICE
     return torch.cuda.device(t.device)
 
 
@@ -249,10 +258,11 @@ class GradArena:
 def arena_of(params):
     """The GradArena that all of `params` are registered with and that still matches their storage, or None."""
     a = getattr(params[0], "_pn_arena", None)
-    if a is None or not a.valid():
+    if a is None:
         return None
-    if any(getattr(p, "_pn_arena", None) is not a or not a.covers(p) for p in params):
-        return None
+    for p in params:
+        if getattr(p, "_pn_arena", None) is not a or not a.covers(p):
+            return None
     return a
 
 
@@ -521,11 +531,12 @@ class FieldFn(torch.autograd.Function):
             # weight gradients: straight into the model's gradient arena where the weight is a registered leaf
             # parameter (the kernel accumulates with atomics); through autograd otherwise (e.g. the fake-quantised W0)
             arena = arena_of(list(tables))
+            if arena is not None:
+                arena.ensure()
             dw, direct = {}, set()
             for k, t in zip(ctx.keys, weights):
                 if (arena is not None and t.is_leaf and t.requires_grad and t.is_contiguous()
                         and getattr(t, "_pn_arena", None) is arena and arena.covers(t)):
-                    arena.ensure()
                     dw[k] = arena.view(t)
                     direct.add(k)
                 else:
