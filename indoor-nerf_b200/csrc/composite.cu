@@ -62,11 +62,14 @@ __device__ __forceinline__ void ray_forward(const float *__restrict__ raw, int C
   }
 }
 
+#ifndef PN_COMP_FWD_MINB
+#define PN_COMP_FWD_MINB 8     // 64 registers: 32 warps per SM hide the scan and exp latency (0.23 -> 0.17 ms at 65536 x 192)
+#endif
 template <int K>
-__global__ void __launch_bounds__(kRayWarps * 32)
+__global__ void __launch_bounds__(kRayWarps * 32, PN_COMP_FWD_MINB)
 composite_fwd_kernel(const float *__restrict__ raw, int C, const float *__restrict__ z,
                      const float *__restrict__ rays_d, const float *__restrict__ noise, int64_t N, int S,
-                     int white, float *__restrict__ rgb, float *__restrict__ disp, float *__restrict__ acc,
+                     int white, int vec4, float *__restrict__ rgb, float *__restrict__ disp, float *__restrict__ acc,
                      float *__restrict__ weights, float *__restrict__ depth, float *__restrict__ sparsity,
                      float *__restrict__ normal) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -83,9 +86,16 @@ composite_fwd_kernel(const float *__restrict__ raw, int C, const float *__restri
         if (weights) weights[r * S + s] = w;
         sw += w;
         swz += w * st.zs[k];
-        c0 += w * sigmoidf(rw[0]);
-        c1 += w * sigmoidf(rw[1]);
-        c2 += w * sigmoidf(rw[2]);
+        float r0, r1, r2;
+        if (vec4) {
+          const float4 v = *reinterpret_cast<const float4 *>(rw);
+          r0 = v.x; r1 = v.y; r2 = v.z;
+        } else {
+          r0 = rw[0]; r1 = rw[1]; r2 = rw[2];
+        }
+        c0 += w * sigmoidf(r0);
+        c1 += w * sigmoidf(r1);
+        c2 += w * sigmoidf(r2);
         if (C == 7) { n0 += w * rw[4]; n1 += w * rw[5]; n2 += w * rw[6]; }
       }
     }
@@ -125,11 +135,14 @@ composite_fwd_kernel(const float *__restrict__ raw, int C, const float *__restri
   }
 }
 
+#ifndef PN_COMP_BWD_MINB
+#define PN_COMP_BWD_MINB 5     // measured: 5 blocks x 4 warps (<= 102 registers) beats 3 (143) and 6 (85, spills)
+#endif
 template <int K>
-__global__ void __launch_bounds__(kRayWarps * 32)
+__global__ void __launch_bounds__(kRayWarps * 32, K <= 6 ? PN_COMP_BWD_MINB : 3)
 composite_bwd_kernel(const float *__restrict__ raw, int C, const float *__restrict__ z,
                      const float *__restrict__ rays_d, const float *__restrict__ noise, int64_t N, int S,
-                     int white, const float *__restrict__ d_rgb, const float *__restrict__ d_disp,
+                     int white, int vec4, const float *__restrict__ d_rgb, const float *__restrict__ d_disp,
                      const float *__restrict__ d_acc, const float *__restrict__ d_weights,
                      const float *__restrict__ d_depth, const float *__restrict__ d_sparsity,
                      const float *__restrict__ d_normal, float *__restrict__ draw) {
@@ -165,6 +178,7 @@ composite_bwd_kernel(const float *__restrict__ raw, int C, const float *__restri
     const float g_den = use_depth ? -g_dep * swz / (sw * sw) : 0.f;
     // entropy
     float g_sp = 0.f, Q = 1.f, Gbar = 0.f, rest_term = 0.f;
+    float Gk[K];                                                      // d entropy / d p_s, kept for the output loop
     if (d_sparsity) {
       g_sp = d_sparsity[r];
       const float rest = fmaxf(1.0f - sw, 1e-6f);
@@ -173,11 +187,12 @@ composite_bwd_kernel(const float *__restrict__ raw, int C, const float *__restri
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int s = k * 32 + lane;
+        Gk[k] = 0.f;
         if (s < S) {
           const float p = st.w[k] / Q;
           const bool in = (p >= FLT_EPSILON) && (p <= 1.0f - FLT_EPSILON);
-          const float G = -(logf(fminf(fmaxf(p, FLT_EPSILON), 1.0f - FLT_EPSILON)) + (in ? 1.0f : 0.f));
-          gq += G * st.w[k];
+          Gk[k] = -(logf(fminf(fmaxf(p, FLT_EPSILON), 1.0f - FLT_EPSILON)) + (in ? 1.0f : 0.f));
+          gq += Gk[k] * st.w[k];
         }
       }
       const float pr = rest / Q;
@@ -203,33 +218,35 @@ composite_bwd_kernel(const float *__restrict__ raw, int C, const float *__restri
         dv0 = g0 / 1e-12f; dv1 = g1 / 1e-12f; dv2 = g2 / 1e-12f;
       }
     }
-    // gradient w.r.t. each weight, then reverse scan for the transmittance chain
-    float gw[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int s = k * 32 + lane;
-      float g = 0.f;
-      if (s < S) {
-        const float *rw = raw + (r * S + s) * C;
-        g = g_acc;
-        if (d_weights) g += d_weights[r * S + s];
-        if (d_rgb) g += gr0 * sigmoidf(rw[0]) + gr1 * sigmoidf(rw[1]) + gr2 * sigmoidf(rw[2]);
-        if (use_depth) g += g_num * st.zs[k] + g_den;
-        if (d_sparsity) {
-          const float p = st.w[k] / Q;
-          const bool in = (p >= FLT_EPSILON) && (p <= 1.0f - FLT_EPSILON);
-          const float G = -(logf(fminf(fmaxf(p, FLT_EPSILON), 1.0f - FLT_EPSILON)) + (in ? 1.0f : 0.f));
-          g += g_sp * ((G / Q - Gbar) - rest_term);
-        }
-        if (has_n) g += dv0 * rw[4] + dv1 * rw[5] + dv2 * rw[6];
-      }
-      gw[k] = g;
-    }
+    // gradient w.r.t. each weight and the reverse scan of the transmittance chain, one 32-sample round at a time from the
+    // far end (the suffix sum only needs the rounds behind it): each sample's colour sigmoids are evaluated once and its
+    // gradient row leaves as one 16-byte store
     float carry = 0.f;
 #pragma unroll
     for (int k = K - 1; k >= 0; --k) {
       const int s = k * 32 + lane;
-      const float v = (s < S) ? gw[k] * st.w[k] : 0.f;
+      const bool valid = s < S;
+      const float *rw = raw + (r * S + s) * C;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, g = 0.f;
+      if (valid) {
+        float c0, c1, c2;
+        if (vec4) {
+          const float4 v = *reinterpret_cast<const float4 *>(rw);
+          c0 = v.x; c1 = v.y; c2 = v.z;
+        } else {
+          c0 = rw[0]; c1 = rw[1]; c2 = rw[2];
+        }
+        g = g_acc;
+        if (d_weights) g += d_weights[r * S + s];
+        if (d_rgb) {
+          s0 = sigmoidf(c0); s1 = sigmoidf(c1); s2 = sigmoidf(c2);
+          g += gr0 * s0 + gr1 * s1 + gr2 * s2;
+        }
+        if (use_depth) g += g_num * st.zs[k] + g_den;
+        if (d_sparsity) g += g_sp * ((Gk[k] / Q - Gbar) - rest_term);
+        if (has_n) g += dv0 * rw[4] + dv1 * rw[5] + dv2 * rw[6];
+      }
+      const float v = valid ? g * st.w[k] : 0.f;
       float incl = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -240,30 +257,41 @@ composite_bwd_kernel(const float *__restrict__ raw, int C, const float *__restri
       if (lane == 31) excl = 0.f;
       const float suffix = excl + carry;                              // sum_{j>s} gw_j w_j
       carry += __shfl_sync(PN_FULL, incl, 0);
-      if (s < S) {
+      if (valid) {
         float *out = draw + (r * S + s) * C;
-        const float *rw = raw + (r * S + s) * C;
-        const float da = gw[k] * st.Tex[k] - suffix / st.t[k];
+        const float da = g * st.Tex[k] - suffix / st.t[k];
         const float sg = st.sg[k];
-        out[3] = (sg > 0.f) ? da * (st.dist[k] * expf(-sg * st.dist[k])) : 0.f;
         const float w = st.w[k];
-        const float s0 = sigmoidf(rw[0]), s1 = sigmoidf(rw[1]), s2 = sigmoidf(rw[2]);
-        out[0] = d_rgb ? gr0 * w * (s0 * (1.0f - s0)) : 0.f;
-        out[1] = d_rgb ? gr1 * w * (s1 * (1.0f - s1)) : 0.f;
-        out[2] = d_rgb ? gr2 * w * (s2 * (1.0f - s2)) : 0.f;
-        if (C == 7) {
-          out[4] = has_n ? w * dv0 : 0.f;
-          out[5] = has_n ? w * dv1 : 0.f;
-          out[6] = has_n ? w * dv2 : 0.f;
+        const float o3 = (sg > 0.f) ? da * (st.dist[k] * expf(-sg * st.dist[k])) : 0.f;
+        const float o0 = d_rgb ? gr0 * w * (s0 * (1.0f - s0)) : 0.f;
+        const float o1 = d_rgb ? gr1 * w * (s1 * (1.0f - s1)) : 0.f;
+        const float o2 = d_rgb ? gr2 * w * (s2 * (1.0f - s2)) : 0.f;
+        if (vec4) {
+          *reinterpret_cast<float4 *>(out) = make_float4(o0, o1, o2, o3);
+        } else {
+          out[0] = o0; out[1] = o1; out[2] = o2; out[3] = o3;
+          if (C == 7) {
+            out[4] = has_n ? w * dv0 : 0.f;
+            out[5] = has_n ? w * dv1 : 0.f;
+            out[6] = has_n ? w * dv2 : 0.f;
+          }
         }
       }
     }
   }
 }
 
-static int ray_blocks(int64_t N) {
+// One resident wave: the ray loop is grid-strided, so a grid of exactly the co-resident blocks (queried per kernel — the
+// backward holds 120+ registers) has no partial last wave.
+template <typename Kern>
+static int ray_blocks(int64_t N, Kern kern) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRayWarps * 32, 0) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 4;
+  }
   const int64_t need = ceil_div(N, kRayWarps);
-  const int64_t cap = (int64_t)sm_count() * 16;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
   return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
@@ -288,10 +316,10 @@ extern "C" int pn_composite_fwd(const float *raw, int channels, const float *z, 
   PN_REQUIRE(channels == 4 || channels == 7, PN_ESHAPE, "channels %d (4 or 7)", channels);
   PN_REQUIRE(n_samples >= 1 && n_samples <= 512, PN_ESHAPE, "n_samples %d outside 1..512", n_samples);
   if (n_rays <= 0) return 0;
-  const int blocks = ray_blocks(n_rays);
+  const int vec4 = channels == 4 && ((uintptr_t)raw & 15) == 0;       // 16-byte rows: one load per sample
 #define CALL(K)                                                                                          \
-  composite_fwd_kernel<K><<<blocks, kRayWarps * 32, 0, as_stream(stream)>>>(                            \
-      raw, channels, z, rays_d, noise, n_rays, n_samples, white_bkgd, rgb, disp, acc, weights, depth, \
+  composite_fwd_kernel<K><<<ray_blocks(n_rays, composite_fwd_kernel<K>), kRayWarps * 32, 0, as_stream(stream)>>>(                            \
+      raw, channels, z, rays_d, noise, n_rays, n_samples, white_bkgd, vec4, rgb, disp, acc, weights, depth, \
       sparsity, normal)
   PN_DISPATCH_K(n_samples, CALL);
 #undef CALL
@@ -308,10 +336,10 @@ extern "C" int pn_composite_bwd(const float *raw, int channels, const float *z, 
   PN_REQUIRE(channels == 4 || channels == 7, PN_ESHAPE, "channels %d (4 or 7)", channels);
   PN_REQUIRE(n_samples >= 1 && n_samples <= 512, PN_ESHAPE, "n_samples %d outside 1..512", n_samples);
   if (n_rays <= 0) return 0;
-  const int blocks = ray_blocks(n_rays);
+  const int vec4 = channels == 4 && (((uintptr_t)raw | (uintptr_t)draw) & 15) == 0;
 #define CALL(K)                                                                                        \
-  composite_bwd_kernel<K><<<blocks, kRayWarps * 32, 0, as_stream(stream)>>>(                          \
-      raw, channels, z, rays_d, noise, n_rays, n_samples, white_bkgd, d_rgb, d_disp, d_acc, d_weights, \
+  composite_bwd_kernel<K><<<ray_blocks(n_rays, composite_bwd_kernel<K>), kRayWarps * 32, 0, as_stream(stream)>>>(                          \
+      raw, channels, z, rays_d, noise, n_rays, n_samples, white_bkgd, vec4, d_rgb, d_disp, d_acc, d_weights, \
       d_depth, d_sparsity, d_normal, draw)
   PN_DISPATCH_K(n_samples, CALL);
 #undef CALL

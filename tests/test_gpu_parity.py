@@ -348,6 +348,18 @@ def test_sample_sort_large(pn):
     assert (s == O.searchsorted_from_cdf(cdf, u, mid)[0]).all()
     merged = pn.ops.sort_merge(z, s)
     assert (merged == torch.sort(torch.cat([z, s], -1), -1)[0]).all()
+    # the other routes through the kernel: sorted second half (det=True), ties between and inside the halves, an
+    # unsorted first half (general path), ragged sizes, a single column
+    s_sorted = torch.sort(s, -1)[0]
+    assert (pn.ops.sort_merge(z, s_sorted) == torch.sort(torch.cat([z, s_sorted], -1), -1)[0]).all()
+    tied = s.clone(); tied[:, :64] = z; tied[:, 64:96] = z[:, :32]
+    assert (pn.ops.sort_merge(z, tied) == torch.sort(torch.cat([z, tied], -1), -1)[0]).all()
+    zu = z[:4096].flip(-1).contiguous()
+    assert (pn.ops.sort_merge(zu, s[:4096]) == torch.sort(torch.cat([zu, s[:4096]], -1), -1)[0]).all()
+    for sa, sb in ((1, 1), (33, 7), (64, 129), (5, 300), (255, 257)):
+        a_ = torch.sort(torch.rand(257, sa, device="cuda", generator=gen), -1)[0]
+        b_ = torch.rand(257, sb, device="cuda", generator=gen)
+        assert (pn.ops.sort_merge(a_, b_) == torch.sort(torch.cat([a_, b_], -1), -1)[0]).all(), (sa, sb)
     # against the oracle's own cdf: mismatching bins are rare and only at ulp-level ties
     _, inds_o, cdf_o = O.sample_pdf(mid, w[:, 1:-1], 128, u=u, return_inds=True)
     diff = inds.long() != inds_o
