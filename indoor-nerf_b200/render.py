@@ -204,12 +204,26 @@ def _write_png(path, img8):
                 chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
 
+_STAGING = {}
+
+
+def _frame_staging(H, W, slots=2):
+    """Pinned host slots for finished frames, kept per frame size: cudaHostAlloc of a test set's worth of frames cost more
+    than rendering one of them (27 of 73 ms per 800x800 frame in round 2's render_path leg)."""
+    key = (H, W, slots)
+    if key not in _STAGING:
+        _STAGING.clear()
+        _STAGING[key] = [(torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True),
+                          torch.empty((H, W), dtype=torch.float32, pin_memory=True)) for _ in range(slots)]
+    return _STAGING[key]
+
+
 def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0, group=None):
     """run_nerf.py:154-215 -> (rgbs [n,H,W,3], depths [n,H,W]) as numpy arrays, depths normalised by near/far.
 
     Differences in HOW, not WHAT: the squared error of every frame is reduced on the device (pn_image_sqerr) and
-    all PSNRs are read back with one transfer at the end instead of a host round trip per frame; frames are
-    copied to pinned host memory asynchronously; with a process group every frame is rendered pixel-sharded
+    all PSNRs are read back with one transfer at the end instead of a host round trip per frame; frames go to
+    two cached pinned slots asynchronously and from there into the result arrays while the next frame renders; with a process group every frame is rendered pixel-sharded
     (row blocks, no collective on the data path, one all-gather of the finished frame).  Saved images are plain
     PNGs of to8b(rgb) and of the normalised depth."""
     import os
@@ -226,14 +240,25 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
     # group=None means "this process renders whole frames", even inside an initialised process group
     world = parallel.world_size(group) if group is not None else 1
     rank = parallel.rank(group) if group is not None else 0
-    pin = dict(pin_memory=True)
-    rgbs = torch.empty((n, H, W, 3), dtype=torch.float32, **pin)
-    depths = torch.empty((n, H, W), dtype=torch.float32, **pin)
+    rgbs = np.empty((n, H, W, 3), dtype=np.float32)
+    depths = np.empty((n, H, W), dtype=np.float32)
+    stage = _frame_staging(H, W)
+    pending = []                                     # (frame, slot, event) whose device->host copy is in flight
+
+    def drain(keep):
+        # finished frames: pinned slot -> the result arrays, on the host while the GPU renders the next frame
+        while len(pending) > keep:
+            j, slot, ev = pending.pop(0)
+            ev.synchronize()
+            np.copyto(rgbs[j], stage[slot][0].numpy())
+            np.copyto(depths[j], stage[slot][1].numpy())
+
     want_psnr = gt_imgs is not None and render_factor == 0
     sq = torch.zeros(n, dtype=torch.float64, device=dev) if want_psnr else None
     rgb8s = []
     with torch.no_grad():
         for i, c2w in enumerate(render_poses):
+            drain(len(stage) - 1)                    # the slot about to be reused has been copied out
             c2w = torch.as_tensor(c2w)[:3, :4]
             if world > 1:
                 ro, rd = get_rays(H, W, K, c2w)
@@ -242,16 +267,20 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
                                                         group=group, gather=True, **kw)
             else:
                 rgb, depth, _, _ = render(H, W, K, chunk=chunk, c2w=c2w, **render_kwargs)
-            rgbs[i].copy_(rgb, non_blocking=True)
+            slot = i % len(stage)
+            stage[slot][0].copy_(rgb, non_blocking=True)
             depth = (depth - near) / (far - near)
-            depths[i].copy_(depth, non_blocking=True)
+            stage[slot][1].copy_(depth, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((i, slot, ev))
             if want_psnr:
                 gt = torch.as_tensor(gt_imgs[i]).to(dev, non_blocking=True).float()
                 ops.image_sqerr(rgb, gt[..., :3], out=sq[i])
             if savedir is not None:
                 rgb8s.append((ops.to8b(rgb).cpu(), ops.to8b(depth).cpu()))
+    drain(0)
     torch.cuda.synchronize(dev)
-    rgbs, depths = rgbs.numpy(), depths.numpy()
     if savedir is not None and rank == 0:
         os.makedirs(savedir, exist_ok=True)
         for i, (c8, d8) in enumerate(rgb8s):
