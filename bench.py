@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 MLP_MODE = os.environ.get("POCKETNERF_MLP", "bf16")     # "bf16": tcgen05 tensor-core NeRFSmall (north_star's 2e-3 mode); "fp32": FFMA
 RAYS = 65536
+USE_GRAPH = True       # Trainer(cuda_graph=True): the iteration is recorded once and replayed (--no-graph: eager step)
 HASH_BYTES_PER_POINT = 12 + 16 * 8 * 2 * 4 + 16 * 2 * 4      # 1164 B/point (hash encode alone)
 # fused field kernels, algorithmic bytes per point: positions 12 + 16 levels x 8 corners x 8 B gathered or
 # scattered (counted once) + the saved bf16 feature tile 64 + raw / cotangent 16 + keep 1
@@ -273,6 +274,7 @@ def structural_consumer_loss(scene, rays, dev):
         d2 = torch.where(ok, depth, prior_depth)
         l_planar = (d2[2:] - 2 * d2[1:-1] + d2[:-2]).abs().mean()          # second differences over neighbouring batch rays
         return 0.001 * l_depth + 0.0002 * l_normal + 0.001 * l_planar       # weights of configs/norcliffe_common_room.txt
+    fn.prior_depth, fn.prior_normal = prior_depth, prior_normal
     return fn
 
 
@@ -294,7 +296,8 @@ def build_workload(name, dev, rank, world, scaling, pn, pmodel, synthetic, Train
     torch.manual_seed(0)                                   # identical initial parameters on every rank
     kw_train, kw_test, _, _, opt = pmodel.create_nerf(a, device=dev)
     torch.manual_seed(1234 + rank)
-    tr = Trainer(a, kw_train, opt, scene["H"], scene["W"], scene["K"], scene["near"], scene["far"], group=group)
+    tr = Trainer(a, kw_train, opt, scene["H"], scene["W"], scene["K"], scene["near"], scene["far"], group=group,
+                 cuda_graph=USE_GRAPH)
     if name == "llff_acaq":
         # A-CAQ past warm-up: table quantisers live (current_step >= warmup_steps), calibrated by the first step, learned
         # soft bit-widths spread over 4..12 as the A-CAQ loop leaves them (run_nerf.py:1225-1252)
@@ -306,11 +309,19 @@ def build_workload(name, dev, rank, world, scaling, pn, pmodel, synthetic, Train
                 q.soft_bits.fill_(float(4.0 + 8.0 * torch.rand((), generator=g)))
     pool = [synthetic.ray_batch(scene, n_rays, seed=1000 * rank + i, pin=True) for i in range(4)]
     pool_dev = [(r.to(dev), t.to(dev)) for r, t in pool]
-    extra = [structural_consumer_loss(scene, r, dev) for r, _ in pool] if name == "scannet_t22" else None
+    extra = None
+    if name == "scannet_t22":
+        # ONE consumer-loss closure over prior buffers that set_batch refills: a recorded iteration (cuda_graph) reads the
+        # current batch's priors, not the ones it was recorded with
+        priors = [[t.to(dev) for t in scene["prior_fn"](r[0], r[1])[1:]] for r, _ in pool]
+        extra = structural_consumer_loss(scene, pool[0][0], dev)
+        tr.extra_loss_fn = extra
 
     def set_batch(i):
         if extra is not None:
-            tr.extra_loss_fn = extra[i % len(extra)]
+            d, nrm = priors[i % len(priors)]
+            extra.prior_depth.copy_(d)
+            extra.prior_normal.copy_(nrm)
     return dict(trainer=tr, pool=pool, pool_dev=pool_dev, set_batch=set_batch, n_rays=n_rays, scene=scene, kw_train=kw_train,
                 kw_test=kw_test, points_per_step=n_rays * (128 + w["n_imp"]), args=a)
 
@@ -332,23 +343,39 @@ def timed_workload(wl, steps, warmup, world, dev, clk=None, want_events=False):
         loss, _ = tr.step(r.to(dev, non_blocking=True), t.to(dev, non_blocking=True))
         losses.append(loss.item())
 
+    # priming, before the W warm-up steps: a graphed trainer records its iteration after GRAPH_WARMUP eager ones
+    if tr.cuda_graph:
+        for i in range(max(0, tr.GRAPH_WARMUP + 1 - tr._eager_steps)):
+            step_e2e(i)
     for i in range(warmup):
         step_e2e(i)
     torch.cuda.synchronize()
     if clk is not None:
         clk.mark_start()
-    if want_events:
-        ops.KERNEL_EVENTS = []
-    l0 = _lib.launch_count()
+    l0, g0 = _lib.launch_count(), tr.graph_launches
     ms = time_steps(step_resident, steps, world)
-    launches = _lib.launch_count() - l0
-    events, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
+    launches = (_lib.launch_count() - l0) + (tr.graph_launches - g0)
+    graphed = tr.graph_launches > g0
     ms_e2e = time_steps(step_e2e, steps, world)
     if clk is not None:
         clk.mark_end()
+    events, n_ev, ms_eager = [], 0, None
+    if want_events:
+        # per-kernel CUDA events: inside the timed region when the step runs eagerly; when it is a replayed CUDA graph
+        # (which cannot carry them) over the same number of eager steps right after it — same kernels, same shapes
+        ops.KERNEL_EVENTS = []
+        n_ev = min(steps, 10)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for i in range(n_ev):
+            step_resident(i)
+        eb.record()
+        torch.cuda.synchronize()
+        events, ops.KERNEL_EVENTS = ops.KERNEL_EVENTS, None
+        ms_eager = ea.elapsed_time(eb) / n_ev
     h2d = pool[0][0].numel() * 4 + pool[0][1].numel() * 4
     return dict(ms=ms, ms_e2e=ms_e2e, launches=launches, h2d=h2d, events=events or [], final_loss=losses[-1] if losses else None,
-                step_resident=step_resident)
+                step_resident=step_resident, graphed=graphed, event_steps=n_ev, ms_eager=ms_eager)
 
 
 def kernel_event_summary(events):
@@ -695,10 +722,18 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": res["ms_e2e"] / args.steps},
         "gpu_launches": int(res["launches"]),
         "final_loss": res["final_loss"],
+        "eager_ms_per_step": res["ms_eager"],
+        "step_mode": ("cuda graph: Trainer(cuda_graph=True) records the whole iteration once (render, losses, backward, "
+                      "all-reduce, RAdam) and replays it; gpu_launches counts the recorded kernels of this package per replay"
+                      if res["graphed"] else "eager Trainer.step"),
     }
     fine_points = n_rays * (64 + WORKLOADS[args.workload]["n_imp"])
     if rank == 0 and MLP_MODE == "bf16":
         line["roofline"] = roofline_block(res["events"], fine_points, hbm_peak, tf_peak, how)
+        if line["roofline"] is not None and res["graphed"]:
+            line["roofline"]["how"] = ("CUDA events on the launching stream around every launch of %d eager steps run right "
+                                       "after the timed region (ops.KERNEL_EVENTS): the timed region replays a CUDA graph, "
+                                       "which cannot carry per-kernel events; same kernels, same shapes" % res["event_steps"])
 
     extras = not args.no_extras
     # ---- legs every rank takes part in --------------------------------------------------------------------------------
@@ -718,7 +753,12 @@ def run_ours(args):
                                             "breakdown_ms": {"field_kernels": field, "allreduce": coll,
                                                              "everything_else": step2 - field - coll,
                                                              "launches_per_step": r2["launches"] / 10,
-                                                             "note": "rank 0, CUDA events inside the timed region; everything_else = "
+                                                             "eager_ms_per_step": r2["ms_eager"],
+                                                             "step_mode": "cuda graph" if r2["graphed"] else "eager",
+                                                             "note": "rank 0; kernel and collective times from CUDA events around "
+                                                                     "every launch of the eager steps run after the timed region "
+                                                                     "(eager_ms_per_step, this rank), ms_per_step from the timed "
+                                                                     "region; everything_else = "
                                                                      "compositing / sampling / TV / RAdam over the full tables / arena "
                                                                      "memset and the host-side launch gaps between ~100 small kernels"}}
             del wl2
@@ -823,8 +863,11 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-baselines", action="store_true", help="skip the reference legs (CPU / eager GPU)")
     ap.add_argument("--no-extras", action="store_true", help="headline + roofline only")
+    ap.add_argument("--no-graph", action="store_true", help="eager Trainer.step (default: Trainer(cuda_graph=True))")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global USE_GRAPH
+    USE_GRAPH = not args.no_graph
     with StdoutToStderr():
         line = run_reference(args) if args.impl == "reference" else run_ours(args)
     if line is not None:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 9
+#define PN_ABI_VERSION 10
 #define PN_MAX_LEVELS 16
 
 #define PN_EINVAL (-1)   /* bad argument */
@@ -266,6 +266,15 @@ int pn_tv_loss_bwd(const float *const *tables, float *const *dtables, int n_leve
 int pn_radam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
                   float beta2, float eps, float weight_decay_times_lr, float step_size_times_lr, int mode,
                   pn_stream_t stream);
+/* The same update with the two per-step scalars read from DEVICE memory: dyn[0] = weight_decay*lr, dyn[1] =
+ * step_size*lr.  For a training step recorded in a CUDA graph (Trainer(cuda_graph=True)): the launch is recorded once,
+ * pn_store_floats refreshes `dyn` before every replay, so the replayed update follows the learning-rate decay
+ * (run_nerf.py:1289-1293) and the rectification term (radam.py:63-78) exactly as the host computes them. */
+int pn_radam_step_dyn(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
+                      float beta2, float eps, const float *dyn, int mode, pn_stream_t stream);
+/* dst[0..n) (device) = values[0..n) (HOST, n <= 16), stream-ordered: the values travel as kernel arguments, so the host
+ * array may be reused as soon as the call returns. */
+int pn_store_floats(float *dst, const float *values, int n, pn_stream_t stream);
 
 /* ---- data formats either side of the path -------------------------------------- */
 

@@ -78,9 +78,13 @@ tv_bwd_kernel(const __grid_constant__ TvArgs A, const int64_t *__restrict__ min_
 
 // radam.py:55-88 on n contiguous elements.  mode 2: rectified adaptive step, 1: SGD-with-momentum step
 // (degenerated_to_sgd), 0: moments only.
+// `dyn` (optional): the two per-step scalars read from device memory — {wd*lr, step_size*lr} — so that a launch recorded
+// in a CUDA graph follows the learning-rate schedule and the rectification term when the graph is replayed.
 __global__ void __launch_bounds__(256)
 radam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-             int64_t n, float beta1, float beta2, float eps, float wd_lr, float step_lr, int mode) {
+             int64_t n, float beta1, float beta2, float eps, float wd_lr, float step_lr, int mode,
+             const float *__restrict__ dyn) {
+  if (dyn != nullptr) { wd_lr = dyn[0]; step_lr = dyn[1]; }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 3 < n) {
@@ -113,6 +117,13 @@ radam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
       }
     }
   }
+}
+
+struct ScalarPack {
+  float v[16];
+};
+__global__ void store_floats_kernel(float *__restrict__ dst, const ScalarPack pack, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = pack.v[threadIdx.x];
 }
 
 }  // namespace pn
@@ -166,7 +177,32 @@ extern "C" int pn_radam_step(float *param, const float *grad, float *exp_avg, fl
   const int64_t need = ceil_div(n, 256 * 4);
   const int64_t cap = (int64_t)sm_count() * 8;
   radam_kernel<<<(unsigned)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, weight_decay_times_lr, step_size_times_lr, mode);
+      param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, weight_decay_times_lr, step_size_times_lr, mode, nullptr);
   count_launch();
   return check_launch("radam_kernel");
+}
+
+extern "C" int pn_radam_step_dyn(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float beta1,
+                                 float beta2, float eps, const float *dyn, int mode, pn_stream_t stream) {
+  PN_REQUIRE(param && grad && exp_avg && exp_avg_sq && dyn, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(mode >= 0 && mode <= 2, PN_EINVAL, "mode %d", mode);
+  PN_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, PN_EINVAL,
+             "buffers must be 16-byte aligned");
+  if (n <= 0) return 0;
+  const int64_t need = ceil_div(n, 256 * 4);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  radam_kernel<<<(unsigned)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, 0.f, 0.f, mode, dyn);
+  count_launch();
+  return check_launch("radam_kernel<dyn>");
+}
+
+extern "C" int pn_store_floats(float *dst, const float *values, int n, pn_stream_t stream) {
+  PN_REQUIRE(dst && values, PN_EINVAL, "NULL pointer argument");
+  PN_REQUIRE(n >= 1 && n <= 16, PN_EINVAL, "n %d outside 1..16", n);
+  ScalarPack pack;
+  for (int i = 0; i < 16; ++i) pack.v[i] = i < n ? values[i] : 0.f;     // host values travel as kernel arguments
+  store_floats_kernel<<<1, 32, 0, as_stream(stream)>>>(dst, pack, n);
+  count_launch();
+  return check_launch("store_floats_kernel");
 }

@@ -331,6 +331,22 @@ def radam_step(p, g, m, v, beta1, beta2, eps, wd_lr, step_lr, mode):
              float(wd_lr), float(step_lr), int(mode), stream())
 
 
+def radam_step_dyn(p, g, m, v, beta1, beta2, eps, dyn, mode):
+    """radam_step with {wd*lr, step_size*lr} read from the device pair `dyn` (a launch that can live in a CUDA graph)."""
+    n = p.numel()
+    with _guard(p):
+        call("pn_radam_step_dyn", dptr(p), dptr(g), dptr(m), dptr(v), n, float(beta1), float(beta2), float(eps),
+             dptr(dyn), int(mode), stream())
+
+
+def store_floats(dst, values):
+    """dst[:len(values)] = values (host floats, at most 16) with one stream-ordered launch and no staging buffer."""
+    import ctypes
+    vals = (ctypes.c_float * len(values))(*values)
+    with _guard(dst):
+        call("pn_store_floats", dptr(dst), vals, len(values), stream())
+
+
 # ---------------------------------------------------------------------------------------------------
 # view directions
 # ---------------------------------------------------------------------------------------------------

@@ -98,7 +98,7 @@ class RAdam(Optimizer):
                 st["exp_avg_sq"] = v[off:off + p.numel()].view_as(p)
                 off += p.numel()
 
-    def _fused_cuda(self, ps, group, step, n_sma, step_size):
+    def _fused_cuda(self, ps, group, step, n_sma, step_size, dyn=None):
         from . import ops
         beta1, beta2 = group["betas"]
         mode = 2 if n_sma >= 5 else (1 if step_size > 0 else 0)
@@ -119,9 +119,60 @@ class RAdam(Optimizer):
                 args = [(p.data.view(-1), p.grad.view(-1), self.state[p]["exp_avg"].view(-1),
                          self.state[p]["exp_avg_sq"].view(-1)) for p in run]
             for pd, gd, m, v in args:
-                ops.radam_step(pd, gd, m, v, beta1, beta2, group["eps"], wd * lr, step_size * lr, mode)
+                if dyn is not None:
+                    ops.radam_step_dyn(pd, gd, m, v, beta1, beta2, group["eps"], dyn, mode)
+                else:
+                    ops.radam_step(pd, gd, m, v, beta1, beta2, group["eps"], wd * lr, step_size * lr, mode)
             if getattr(self, "_recording", None) is not None:
                 self._recording += args
+
+    # ---- a step recorded in a CUDA graph (Trainer(cuda_graph=True)) ------------------------------------------------
+    def _graph_groups(self):
+        """[(group, live parameters)] when every parameter with a gradient can take the fused update in its rectified
+        form (state initialised, N_sma >= 5 from here on), else None."""
+        out = []
+        for group in self.param_groups:
+            live = [p for p in group["params"] if p.grad is not None]
+            if not live:
+                out.append((group, live))
+                continue
+            if not all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and not p.grad.is_sparse
+                       and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and len(self.state[p]) > 0
+                       for p in live):
+                return None
+            steps = {self.state[p]["step"] for p in live}
+            beta1, beta2 = group["betas"]
+            if len(steps) != 1 or self._rectification(steps.pop() + 1, beta1, beta2, self.degenerated_to_sgd)[0] < 5:
+                return None
+            out.append((group, live))
+        return out
+
+    def graph_capture_step(self, dyn):
+        """The launches of one update with the per-step scalars in dyn[group] = {wd*lr, step_size*lr} (device): called
+        while the stream is capturing; touches no optimiser state."""
+        for gi, (group, live) in enumerate(self._graph_groups()):
+            if live:
+                self._fused_cuda(live, group, None, 5, 1.0, dyn=dyn[gi])
+
+    def graph_advance(self):
+        """Host side of one replay: advances every 'step' counter and returns the scalars of this update, flattened per
+        group ([wd*lr, step_size*lr, ...]) as radam.py:63-85 computes them — or None when the update would not be the
+        rectified one the graph recorded."""
+        groups = self._graph_groups()
+        if groups is None:
+            return None
+        vals = []
+        for group, live in groups:
+            if not live:
+                vals += [0.0, 0.0]
+                continue
+            beta1, beta2 = group["betas"]
+            step = self.state[live[0]]["step"] + 1
+            for p in live:
+                self.state[p]["step"] = step
+            _, step_size = self._rectification(step, beta1, beta2, self.degenerated_to_sgd)
+            vals += [group["weight_decay"] * group["lr"], step_size * group["lr"]]
+        return vals
 
     def _plan_key(self, live):
         st = self.state

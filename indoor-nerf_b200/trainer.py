@@ -11,10 +11,20 @@ from .run_nerf_helpers import img2mse, mse2psnr
 
 
 class Trainer:
-    def __init__(self, args, render_kwargs_train, optimizer, H, W, K, near, far, group=None, start=0):
+    GRAPH_WARMUP = 8        # eager steps before a capture: lazy allocations done, RAdam past N_sma >= 5 (step 6)
+
+    def __init__(self, args, render_kwargs_train, optimizer, H, W, K, near, far, group=None, start=0, cuda_graph=False):
         """`start` is create_nerf's third return value (the checkpoint's global_step, run_nerf.py:299): the learning-rate
         decay and the TV cut-off continue from it after a resume.  `group=None` means a single-process trainer even
-        inside an initialised process group (same convention as RayBank / render_path); pass the group to shard."""
+        inside an initialised process group (same convention as RayBank / render_path); pass the group to shard.
+
+        `cuda_graph=True`: after GRAPH_WARMUP eager steps the whole iteration — render, losses, backward, the gradient
+        all-reduce, RAdam — is recorded once per (batch shape, TV on/off) as a CUDA graph and replayed; per step the host
+        copies the batch into the graph's input buffers, stores RAdam's two scalars per group and launches the graph
+        (~0.1 ms instead of ~3 ms of Python and ~150 launches: what bounds the step at small per-GPU batches, i.e. strong
+        scaling).  Same arithmetic and same use of torch's CUDA generator as the eager step.  Falls back to the eager
+        step while quantisers are in play (their calibration and bit schedule are host logic) or when the optimiser is
+        not this package's RAdam on CUDA."""
         self.args, self.kw, self.opt = args, dict(render_kwargs_train), optimizer
         self.H, self.W, self.K, self.near, self.far = H, W, K, near, far
         self.group = group
@@ -25,6 +35,10 @@ class Trainer:
         self.nets = [self.kw["network_fn"]] + ([self.kw["network_fine"]] if self.kw.get("network_fine") is not None else [])
         self._uncalibrated = [q for q in parallel.model_quantizers(self.embed_fn, self.nets) if not q.calibrated]
         self.extra_loss_fn = None
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None                                         # dict: key, graph, static inputs / outputs, dyn
+        self._eager_steps = 0
+        self.graph_launches = 0                                    # kernels of this package launched by graph replays
         if self.step_idx > 0:
             self.decay_learning_rate(self.step_idx)                # the lr of the iteration about to run
 
@@ -47,6 +61,77 @@ class Trainer:
 
     def step(self, batch_rays, target_s, chunk=None):
         """batch_rays [2,N,3], target_s [N,3] (this rank's shard).  Returns (loss, psnr) as 0-d device tensors."""
+        if self.cuda_graph and self._eager_steps >= self.GRAPH_WARMUP:
+            out = self._step_graphed(batch_rays, target_s, chunk)
+            if out is not None:
+                return out
+        self._eager_steps += 1
+        return self._step_eager(batch_rays, target_s, chunk)
+
+    # ---- the iteration as a CUDA graph ----------------------------------------------------------------------------
+    def _graph_eligible(self):
+        from . import ops
+        if ops.KERNEL_EVENTS is not None or not hasattr(self.opt, "graph_capture_step"):
+            return False
+        if getattr(self.embed_fn, "use_quantization", False) or any(getattr(n, "use_quantization", False) for n in self.nets):
+            return False
+        return self.opt._graph_groups() is not None
+
+    def _capture(self, batch_rays, target_s, chunk, key):
+        from . import _lib
+        l0 = _lib.launch_count()
+        g = {"key": key, "rays": batch_rays.detach().clone(), "target": target_s.detach().clone(),
+             "dyn": torch.zeros((len(self.opt.param_groups), 2), dtype=torch.float32, device=batch_rays.device),
+             "log10": torch.log(torch.tensor([10.], device=batch_rays.device))}   # mse2psnr's divisor, made outside the capture
+        step_before = self.embed_fn.current_step
+        graph = torch.cuda.CUDAGraph()
+        # thread_local: a process group's watchdog thread may query its events while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            rgb, depth, acc, extras = render(self.H, self.W, self.K, chunk=chunk or batch_rays.shape[1], rays=g["rays"],
+                                             retraw=True, near=self.near, far=self.far, **self.kw)
+            self.opt.zero_grad()
+            loss, img_loss = self.losses(rgb, extras, g["target"], depth)
+            loss.backward()
+            if self.world > 1:
+                parallel.allreduce_gradients(self.embed_fn, self.nets, self.group)
+            self.opt.graph_capture_step(g["dyn"])
+            psnr = -10. * torch.log(img_loss.detach()) / g["log10"]             # mse2psnr, run_nerf_helpers.py:15
+            g["out"] = torch.cat([loss.detach().reshape(1), psnr.reshape(1)])
+        g["steps_per_iter"] = self.embed_fn.current_step - step_before     # hash_encoding.py:83-84, per network call
+        self.embed_fn.current_step = step_before                           # recording is not an iteration
+        g["graph"] = graph
+        g["launches"] = _lib.launch_count() - l0                           # this package's kernels in one replay
+        return g
+
+    def _step_graphed(self, batch_rays, target_s, chunk):
+        from . import ops
+        if not self._graph_eligible():
+            return None
+        key = (tuple(batch_rays.shape), tuple(target_s.shape), chunk, self.tv_weight, self.world, id(self.extra_loss_fn))
+        if self._graph is None or self._graph["key"] != key:
+            self._graph = None                                     # release the old graph's pool first
+            self._graph = self._capture(batch_rays, target_s, chunk, key)
+        g = self._graph
+        vals = self.opt.graph_advance()
+        if vals is None:
+            return None
+        g["rays"].copy_(batch_rays, non_blocking=True)
+        g["target"].copy_(target_s, non_blocking=True)
+        ops.store_floats(g["dyn"], vals)
+        g["graph"].replay()
+        self.graph_launches += g["launches"] + 1                   # + the scalar store above
+        self.embed_fn.current_step += g["steps_per_iter"]
+        out = g["out"].clone()
+        self._end_of_iteration()
+        return out[0], out[1:2]                                    # shapes of the eager step: loss 0-d, psnr [1]
+
+    def _end_of_iteration(self):
+        self.step_idx += 1
+        if self.step_idx > 1000:                                   # run_nerf.py:1036-1037
+            self.tv_weight = 0.0
+        self.decay_learning_rate(self.step_idx - 1)
+
+    def _step_eager(self, batch_rays, target_s, chunk=None):
         rgb, depth, acc, extras = render(self.H, self.W, self.K, chunk=chunk or batch_rays.shape[1], rays=batch_rays,
                                          retraw=True, near=self.near, far=self.far, **self.kw)
         self._sync_fresh_quantizers()
@@ -64,10 +149,7 @@ class Trainer:
             else:
                 parallel.allreduce_gradients(self.embed_fn, self.nets, self.group)
         self.opt.step()
-        self.step_idx += 1
-        if self.step_idx > 1000:                                   # run_nerf.py:1036-1037
-            self.tv_weight = 0.0
-        self.decay_learning_rate(self.step_idx - 1)
+        self._end_of_iteration()
         return loss.detach(), mse2psnr(img_loss.detach())
 
     def _sync_fresh_quantizers(self):

@@ -145,3 +145,83 @@ def test_resume_continues_learning_rate_and_tv_cutoff():
         assert all(abs(g["lr"] - want) < 1e-12 for g in opt2.param_groups)            # lr(1500) again: global_step repeats on resume
         assert torch.equal(kw2["embed_fn"].embeddings[3].weight.detach() != kw["embed_fn"].embeddings[3].weight.detach(),
                            kw2["embed_fn"].embeddings[3].weight.detach() != kw["embed_fn"].embeddings[3].weight.detach())
+
+
+def _train_graph_pair(cuda_graph, steps, scene, perturb, n_rays=2048):
+    """bf16 training through Trainer(cuda_graph=...) with identical seeds; returns losses, psnrs, final MLP weights, the
+    table storage, the trainer and the optimiser."""
+    import indoor_nerf_b200 as pn
+    from indoor_nerf_b200 import model as pmodel, synthetic
+    from indoor_nerf_b200.trainer import Trainer
+    dev = torch.device("cuda", 0)
+    a = pmodel.default_args(bounding_box=scene["bounding_box"], lrate=0.01, log2_hashmap_size=LOG2T, perturb=perturb)
+    torch.manual_seed(7)
+    kw, _, _, _, opt = pmodel.create_nerf(a, device=dev)
+    kw["perturb"] = perturb
+    tr = Trainer(a, kw, opt, scene["H"], scene["W"], scene["K"], scene["near"], scene["far"], cuda_graph=cuda_graph)
+    pn.set_mlp_mode("bf16")
+    losses, psnrs = [], []
+    try:
+        torch.manual_seed(8)
+        for i in range(steps):
+            r, t = synthetic.ray_batch(scene, n_rays, seed=i, device=dev)
+            loss, psnr = tr.step(r, t)
+            assert loss.shape == () and psnr.shape == (1,)
+            losses.append(loss)
+            psnrs.append(psnr[0])
+    finally:
+        pn.set_mlp_mode("fp32")
+    w = torch.cat([p.detach().reshape(-1) for n in (kw["network_fn"], kw["network_fine"]) for p in n.parameters()])
+    return (torch.stack(losses).cpu().numpy(), torch.stack(psnrs).cpu().numpy(), w.cpu().numpy(),
+            kw["embed_fn"].table_storage.detach().cpu().numpy(), tr, opt)
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """Trainer(cuda_graph=True): 8 eager iterations, then the recorded iteration replayed.  Without stratified jitter the
+    step is deterministic up to the order of the floating-point reductions, so the graphed run must follow the eager one
+    to rounding: same losses, same weights and tables after 30 iterations (lr decay and RAdam's rectification term are
+    fed to the graph per replay), same host-side counters."""
+    from indoor_nerf_b200.trainer import Trainer
+    scene = _scene()
+    le, pe, we, te, tr_e, opt_e = _train_graph_pair(False, 30, scene, perturb=0.0)
+    lg, pg, wg, tg, tr_g, opt_g = _train_graph_pair(True, 30, scene, perturb=0.0)
+    assert tr_g._graph is not None and tr_g._eager_steps == Trainer.GRAPH_WARMUP, "the graph path did not run"
+    assert np.array_equal(le[:8], lg[:8]) or np.allclose(le[:8], lg[:8], rtol=1e-5)
+    assert np.allclose(le, lg, rtol=2e-3), np.abs(le / lg - 1).max()
+    assert np.allclose(pe, pg, rtol=2e-3, atol=2e-3)
+    # RAdam's normalised update turns reduction-order noise on a near-zero gradient into a full +-lr move, so single
+    # elements drift apart at the rate two eager runs do; the bulk must agree to rounding
+    for e, g, name in ((we, wg, "weights"), (te, tg, "tables")):
+        d, scale = np.abs(e - g), np.abs(e).max()
+        assert np.median(d) <= 1e-4 * scale and np.quantile(d, 0.99) <= 2e-3 * scale and d.max() <= 3e-2 * scale, \
+            (name, np.median(d), np.quantile(d, 0.99), d.max(), scale)
+    assert tr_e.step_idx == tr_g.step_idx == 30
+    assert tr_e.embed_fn.current_step == tr_g.embed_fn.current_step
+    for ge, gg in zip(opt_e.param_groups, opt_g.param_groups):
+        assert ge["lr"] == gg["lr"]
+        assert [opt_e.state[p]["step"] for p in ge["params"] if p in opt_e.state] == \
+               [opt_g.state[p]["step"] for p in gg["params"] if p in opt_g.state]
+
+
+def test_cuda_graph_step_draws_fresh_randomness():
+    """With stratified jitter the replayed graph must draw NEW uniforms every iteration (torch's CUDA generator is
+    registered with the capture): feeding the same batch twice gives different losses, and training still converges
+    like the eager run."""
+    scene = _scene()
+    le, _, _, _, _, _ = _train_graph_pair(False, 60, scene, perturb=1.0)
+    lg, _, _, _, tr, _ = _train_graph_pair(True, 60, scene, perturb=1.0)
+    assert tr._graph is not None
+    assert abs(np.log(le[40:].mean() / lg[40:].mean())) < 0.25, (le[40:].mean(), lg[40:].mean())
+    from indoor_nerf_b200 import synthetic
+    import indoor_nerf_b200 as pn
+    r, t = synthetic.ray_batch(scene, 2048, seed=0, device=torch.device("cuda", 0))
+    pn.set_mlp_mode("bf16")
+    try:
+        for g in tr.opt.param_groups:
+            g["lr"] = 0.0
+        tr.args.lrate = 0.0
+        a = float(tr.step(r, t)[0])
+        b = float(tr.step(r, t)[0])
+    finally:
+        pn.set_mlp_mode("fp32")
+    assert a != b and abs(a - b) < 0.2 * abs(a)
