@@ -364,6 +364,11 @@ def timed_workload(wl, steps, warmup, world, dev, clk=None, want_events=False):
         # per-kernel CUDA events: inside the timed region when the step runs eagerly; when it is a replayed CUDA graph
         # (which cannot carry them) over the same number of eager steps right after it — same kernels, same shapes
         ops.KERNEL_EVENTS = []
+        if graphed:
+            for i in range(2):                      # the capture emptied the caching allocator: refill it, untimed
+                step_resident(i)
+            torch.cuda.synchronize()
+            ops.KERNEL_EVENTS = []
         n_ev = min(steps, 10)
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record()
@@ -685,6 +690,7 @@ def short_workload_leg(name, dev, rank, world, scaling, mods, group, steps=6, wa
         if name == "llff_acaq":
             out["table_quantisers"] = {"calibrated": all(q.calibrated for q in emb.quantizers),
                                        "soft_bits": [round(float(q.soft_bits), 2) for q in emb.quantizers]}
+        wl["trainer"].release_graph()
         del wl
         torch.cuda.empty_cache()
         return out
@@ -761,6 +767,7 @@ def run_ours(args):
                                                                      "region; everything_else = "
                                                                      "compositing / sampling / TV / RAdam over the full tables / arena "
                                                                      "memset and the host-side launch gaps between ~100 small kernels"}}
+            wl2["trainer"].release_graph()
             del wl2
             torch.cuda.empty_cache()
         except Exception as ex:
@@ -807,8 +814,13 @@ def run_ours(args):
             line["render"] = {"error": repr(ex)}
         torch.cuda.empty_cache()
     if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        # recorded iterations hold NCCL work: they must be gone before the communicator is (main() tears it down after the
+        # JSON line is out; destroying the process group under a live graph hung the 2-GPU run of round 2)
+        wl["trainer"].release_graph()
+        del wl
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
     if rank == 0 and world == 1 and not args.no_baselines and args.workload == "chair":
         # ---- the reference's own eager path on this GPU (denominator of the >= 50x target) and on the host cores ------
         del wl
@@ -872,6 +884,26 @@ def main():
         line = run_reference(args) if args.impl == "reference" else run_ours(args)
     if line is not None:
         emit(line)
+    finish_distributed()
+
+
+def finish_distributed():
+    """Barrier + process-group teardown AFTER the result is out, under a watchdog: a teardown that does not return within
+    60 s ends the process with exit code 0 (the measurement is complete and printed; nothing of value is lost)."""
+    import threading
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    dog = threading.Timer(60.0, lambda: os._exit(0))
+    dog.daemon = True
+    dog.start()
+    try:
+        with StdoutToStderr():
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+    finally:
+        dog.cancel()
 
 
 if __name__ == "__main__":

@@ -125,6 +125,13 @@ class Trainer:
         self._end_of_iteration()
         return out[0], out[1:2]                                    # shapes of the eager step: loss 0-d, psnr [1]
 
+    def release_graph(self):
+        """Drop the recorded iteration (its memory pool and, with a process group, the collective it holds).  Call before
+        destroying the process group: a communicator must outlive every graph that recorded work on it."""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+
     def _end_of_iteration(self):
         self.step_idx += 1
         if self.step_idx > 1000:                                   # run_nerf.py:1036-1037
