@@ -107,7 +107,8 @@ class Trainer:
         from . import ops
         if not self._graph_eligible():
             return None
-        key = (tuple(batch_rays.shape), tuple(target_s.shape), chunk, self.tv_weight, self.world, id(self.extra_loss_fn))
+        key = (tuple(batch_rays.shape), tuple(target_s.shape), chunk, self.tv_weight, self.world, id(self.extra_loss_fn),
+               ops.get_mlp_mode())
         if self._graph is None or self._graph["key"] != key:
             self._graph = None                                     # release the old graph's pool first
             self._graph = self._capture(batch_rays, target_s, chunk, key)
