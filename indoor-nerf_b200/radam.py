@@ -147,6 +147,16 @@ class RAdam(Optimizer):
             out.append((group, live))
         return out
 
+    def graph_fingerprint(self, groups):
+        """Every address a recorded update touches (parameters, gradients, both moments): a recorded iteration is only
+        valid while none of them moved (load_state_dict, a re-flattened table set, a released gradient arena ...)."""
+        fp = []
+        for _, live in groups:
+            for p in live:
+                st = self.state[p]
+                fp.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()))
+        return hash(tuple(fp))
+
     def graph_capture_step(self, dyn):
         """The launches of one update with the per-step scalars in dyn[group] = {wd*lr, step_size*lr} (device): called
         while the stream is capturing; touches no optimiser state."""
@@ -154,11 +164,11 @@ class RAdam(Optimizer):
             if live:
                 self._fused_cuda(live, group, None, 5, 1.0, dyn=dyn[gi])
 
-    def graph_advance(self):
+    def graph_advance(self, groups=None):
         """Host side of one replay: advances every 'step' counter and returns the scalars of this update, flattened per
         group ([wd*lr, step_size*lr, ...]) as radam.py:63-85 computes them — or None when the update would not be the
         rectified one the graph recorded."""
-        groups = self._graph_groups()
+        groups = groups if groups is not None else self._graph_groups()
         if groups is None:
             return None
         vals = []

@@ -69,13 +69,14 @@ class Trainer:
         return self._step_eager(batch_rays, target_s, chunk)
 
     # ---- the iteration as a CUDA graph ----------------------------------------------------------------------------
-    def _graph_eligible(self):
+    def _graph_groups(self):
+        """The optimiser's (group, live parameters) list when this iteration may run as a recorded graph, else None."""
         from . import ops
         if ops.KERNEL_EVENTS is not None or not hasattr(self.opt, "graph_capture_step"):
-            return False
+            return None
         if getattr(self.embed_fn, "use_quantization", False) or any(getattr(n, "use_quantization", False) for n in self.nets):
-            return False
-        return self.opt._graph_groups() is not None
+            return None
+        return self.opt._graph_groups()
 
     def _capture(self, batch_rays, target_s, chunk, key):
         from . import _lib
@@ -105,15 +106,23 @@ class Trainer:
 
     def _step_graphed(self, batch_rays, target_s, chunk):
         from . import ops
-        if not self._graph_eligible():
+        groups = self._graph_groups()
+        if groups is None:
             return None
         key = (tuple(batch_rays.shape), tuple(target_s.shape), chunk, self.tv_weight, self.world, id(self.extra_loss_fn),
-               ops.get_mlp_mode())
+               ops.get_mlp_mode(), self.opt.graph_fingerprint(groups))
         if self._graph is None or self._graph["key"] != key:
             self._graph = None                                     # release the old graph's pool first
-            self._graph = self._capture(batch_rays, target_s, chunk, key)
+            g = self._capture(batch_rays, target_s, chunk, key)
+            # the recorded backward may have given parameters outside the gradient arena new .grad tensors: the key the
+            # next step computes must be the one this graph is filed under
+            groups = self._graph_groups()
+            if groups is None:
+                return None
+            g["key"] = key[:-1] + (self.opt.graph_fingerprint(groups),)
+            self._graph = g
         g = self._graph
-        vals = self.opt.graph_advance()
+        vals = self.opt.graph_advance(groups)
         if vals is None:
             return None
         g["rays"].copy_(batch_rays, non_blocking=True)

@@ -212,6 +212,29 @@ def test_cuda_graph_step_equals_eager_step():
                [opt_g.state[p]["step"] for p in gg["params"] if p in opt_g.state]
 
 
+def test_cuda_graph_rerecords_when_optimizer_state_moves():
+    """load_state_dict gives RAdam new moment tensors: the recorded iteration must not keep updating the old ones."""
+    import indoor_nerf_b200 as pn
+    from indoor_nerf_b200 import synthetic
+    scene = _scene()
+    _, _, _, _, tr, opt = _train_graph_pair(True, 14, scene, perturb=0.0)
+    first = tr._graph["graph"]
+    p0 = opt.param_groups[0]["params"][0]
+    import copy
+    opt.load_state_dict(copy.deepcopy(opt.state_dict()))          # as after torch.load: fresh tensors
+    m_new = opt.state[p0]["exp_avg"]
+    before = m_new.clone()
+    pn.set_mlp_mode("bf16")
+    try:
+        r, t = synthetic.ray_batch(scene, 2048, seed=99, device=torch.device("cuda", 0))
+        loss, _ = tr.step(r, t)
+    finally:
+        pn.set_mlp_mode("fp32")
+    assert tr._graph["graph"] is not first, "the stale graph was replayed"
+    assert torch.isfinite(loss) and not torch.equal(m_new, before), "the live moments were not updated"
+    assert opt.state[p0]["step"] == 15
+
+
 def test_cuda_graph_step_draws_fresh_randomness():
     """With stratified jitter the replayed graph must draw NEW uniforms every iteration (torch's CUDA generator is
     registered with the capture): feeding the same batch twice gives different losses, and training still converges
