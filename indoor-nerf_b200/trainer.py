@@ -22,9 +22,9 @@ class Trainer:
         all-reduce, RAdam — is recorded once per (batch shape, TV on/off) as a CUDA graph and replayed; per step the host
         copies the batch into the graph's input buffers, stores RAdam's two scalars per group and launches the graph
         (~0.1 ms instead of ~3 ms of Python and ~150 launches: what bounds the step at small per-GPU batches, i.e. strong
-        scaling).  Same arithmetic and same use of torch's CUDA generator as the eager step.  Falls back to the eager
-        step while quantisers are in play (their calibration and bit schedule are host logic) or when the optimiser is
-        not this package's RAdam on CUDA."""
+        scaling).  Same arithmetic and same use of torch's CUDA generator as the eager step.  Runs the eager step
+        while quantisers are in play (their calibration and bit schedule are host logic) or when the optimiser is not
+        this package's RAdam on CUDA; a consumer loss that synchronises with the host cannot be recorded and raises."""
         self.args, self.kw, self.opt = args, dict(render_kwargs_train), optimizer
         self.H, self.W, self.K, self.near, self.far = H, W, K, near, far
         self.group = group
@@ -87,19 +87,21 @@ class Trainer:
         step_before = self.embed_fn.current_step
         graph = torch.cuda.CUDAGraph()
         # thread_local: a process group's watchdog thread may query its events while this thread captures
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            rgb, depth, acc, extras = render(self.H, self.W, self.K, chunk=chunk or batch_rays.shape[1], rays=g["rays"],
-                                             retraw=True, near=self.near, far=self.far, **self.kw)
-            self.opt.zero_grad()
-            loss, img_loss = self.losses(rgb, extras, g["target"], depth)
-            loss.backward()
-            if self.world > 1:
-                parallel.allreduce_gradients(self.embed_fn, self.nets, self.group)
-            self.opt.graph_capture_step(g["dyn"])
-            psnr = -10. * torch.log(img_loss.detach()) / g["log10"]             # mse2psnr, run_nerf_helpers.py:15
-            g["out"] = torch.cat([loss.detach().reshape(1), psnr.reshape(1)])
-        g["steps_per_iter"] = self.embed_fn.current_step - step_before     # hash_encoding.py:83-84, per network call
-        self.embed_fn.current_step = step_before                           # recording is not an iteration
+        try:
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                rgb, depth, acc, extras = render(self.H, self.W, self.K, chunk=chunk or batch_rays.shape[1], rays=g["rays"],
+                                                 retraw=True, near=self.near, far=self.far, **self.kw)
+                self.opt.zero_grad()
+                loss, img_loss = self.losses(rgb, extras, g["target"], depth)
+                loss.backward()
+                if self.world > 1:
+                    parallel.allreduce_gradients(self.embed_fn, self.nets, self.group)
+                self.opt.graph_capture_step(g["dyn"])
+                psnr = -10. * torch.log(img_loss.detach()) / g["log10"]         # mse2psnr, run_nerf_helpers.py:15
+                g["out"] = torch.cat([loss.detach().reshape(1), psnr.reshape(1)])
+            g["steps_per_iter"] = self.embed_fn.current_step - step_before  # hash_encoding.py:83-84, per network call
+        finally:
+            self.embed_fn.current_step = step_before                        # recording is not an iteration
         g["graph"] = graph
         g["launches"] = _lib.launch_count() - l0                           # this package's kernels in one replay
         return g
@@ -113,7 +115,14 @@ class Trainer:
                ops.get_mlp_mode(), self.opt.graph_fingerprint(groups))
         if self._graph is None or self._graph["key"] != key:
             self._graph = None                                     # release the old graph's pool first
-            g = self._capture(batch_rays, target_s, chunk, key)
+            try:
+                g = self._capture(batch_rays, target_s, chunk, key)
+            except Exception as ex:
+                # e.g. a consumer loss that synchronises with the host.  No silent fallback: a capture that died half way
+                # leaves torch's CUDA generator registered with it, so the process is not in a state to train on
+                self.cuda_graph = False
+                raise RuntimeError("Trainer(cuda_graph=True): the iteration could not be recorded as a CUDA graph (%r); "
+                                   "construct the Trainer with cuda_graph=False for this configuration" % (ex,)) from ex
             # the recorded backward may have given parameters outside the gradient arena new .grad tensors: the key the
             # next step computes must be the one this graph is filed under
             groups = self._graph_groups()
