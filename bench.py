@@ -345,8 +345,21 @@ def timed_workload(wl, steps, warmup, world, dev, clk=None, want_events=False):
 
     # priming, before the W warm-up steps: a graphed trainer records its iteration after GRAPH_WARMUP eager ones
     if tr.cuda_graph:
-        for i in range(max(0, tr.GRAPH_WARMUP + 1 - tr._eager_steps)):
-            step_e2e(i)
+        try:
+            if os.environ.get("PN_BENCH_FORCE_GRAPH_FAILURE"):          # test hook for the restart below
+                raise RuntimeError("forced by PN_BENCH_FORCE_GRAPH_FAILURE")
+            for i in range(max(0, tr.GRAPH_WARMUP + 1 - tr._eager_steps)):
+                step_e2e(i)
+        except RuntimeError as ex:
+            # A recording that fails leaves torch's CUDA generator tied to the dead capture: measure the eager step in a
+            # fresh process image instead of reporting nothing (every rank takes this branch: the failure is in code all
+            # ranks run identically).
+            sys.stderr.write("bench.py: recording the iteration failed (%r); restarting with --no-graph\n" % (ex,))
+            sys.stderr.flush()
+            env = dict(os.environ)
+            env.pop("PN_BENCH_FORCE_GRAPH_FAILURE", None)
+            StdoutToStderr.restore_for_exec()
+            os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + ["--no-graph"], env)
     for i in range(warmup):
         step_e2e(i)
     torch.cuda.synchronize()
@@ -851,16 +864,27 @@ class StdoutToStderr:
     """Everything written to fd 1 while active goes to stderr (NCCL prints its version banner on stdout), so
     that the ONE JSON line is the only thing this program ever writes to stdout."""
 
+    active = None
+
     def __enter__(self):
         sys.stdout.flush()
         self.saved = os.dup(1)
         os.dup2(2, 1)
+        StdoutToStderr.active = self
         return self
 
     def __exit__(self, *a):
         sys.stdout.flush()
         os.dup2(self.saved, 1)
         os.close(self.saved)
+        StdoutToStderr.active = None
+
+    @staticmethod
+    def restore_for_exec():
+        """Put the real stdout back on fd 1 (a process image started by exec inherits the descriptors)."""
+        if StdoutToStderr.active is not None:
+            sys.stdout.flush()
+            os.dup2(StdoutToStderr.active.saved, 1)
 
 
 def emit(line):
