@@ -644,7 +644,7 @@ def io_legs(pn, scene, kw2, scene2, dev):
 
 
 def render_t22_leg(pn, pmodel, synthetic, dev):
-    """Test-view rendering at log2_hashmap 22 with an 8-bit A-CAQ model: fp32 tables, fake-quant in the gather, u8 codes."""
+    """Test-view rendering at log2_hashmap 22 with an 8-bit A-CAQ model: fp32 tables, fake-quantised tables, u8 codes."""
     try:
         sc = synthetic.blender_scene(800, 800, n_views=2)
         a = pmodel.default_args(bounding_box=sc["bounding_box"], finest_res=1024, log2_hashmap_size=22,
@@ -678,7 +678,7 @@ def render_t22_leg(pn, pmodel, synthetic, dev):
         emb.use_quantization = False
         out["fp32_tables_mpix_per_s"], _ = mpix()
         emb.use_quantization = True
-        out["fake_quant_in_gather_mpix_per_s"], img_fq = mpix()
+        out["fake_quant_tables_mpix_per_s"], img_fq = mpix()     # pn_table_fake_quant per chunk, then the plain gather
         packed = emb.pack_for_inference()
         out["u8_codes_mpix_per_s"], img_pk = mpix()
         out["max_abs_frame_diff_codes_vs_fake_quant"] = float((img_fq - img_pk).abs().max())

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 10
+#define PN_ABI_VERSION 11
 #define PN_MAX_LEVELS 16
 
 #define PN_EINVAL (-1)   /* bad argument */
@@ -86,6 +86,14 @@ int pn_hash_indices(const pn_hash_grid *grid, const float *x, int64_t n_points, 
  * (loss.py:29).  out[n] int64. */
 int pn_hash_coords(const int64_t *coords, int64_t n, int dim, int log2_hashmap_size, int64_t *out,
                    pn_stream_t stream);
+
+/* out[l][i] = LearnedBitwidthQuantizer.forward(tables[l][i]) with level l's row of qparams (quantization.py:177-187), or
+ * a copy where the row is disabled: the fake-quant of hash_encoding.py:97-101 hoisted from the gathered corner values to
+ * the table entries.  Bit-identical to passing `qparams` to pn_hash_encode_fwd / pn_field_fwd_bf16 on the original tables
+ * (in the exact IEEE-division form for both arithmetic modes), at L x T x 2 quantiser evaluations per call instead of
+ * 16 x 8 x 2 per point.  tables[l], out[l]: device [entries_per_level, 2] fp32, 16-byte aligned; may not alias. */
+int pn_table_fake_quant(const float *const *tables, float *const *out, int n_levels, int64_t entries_per_level,
+                        const float *qparams, pn_stream_t stream);
 
 /* Per-level min and max of the gathered corner values, minmax[n_levels][2] (caller initialises
  * to +inf/-inf) — the batch statistics LearnedBitwidthQuantizer.calibrate reads

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # POCKETNERF_LIB selects another build of the same sources (tuning experiments: csrc/build.sh with PN_NVCC_EXTRA)
 LIB_PATH = os.environ.get("POCKETNERF_LIB") or os.path.join(_HERE, "csrc", "libpocketnerf.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_LEVELS = 16
 QROW = 8
 
@@ -65,6 +65,7 @@ _SIGNATURES = {
     "pn_tv_loss_fwd": [_P, _I, _I, _P, _P, _P, _P],
     "pn_tv_loss_bwd": [_P, _P, _I, _I, _P, _P, _P, _P],
     "pn_radam_step": [_P, _P, _P, _P, _L] + [ctypes.c_float] * 5 + [_I, _P],
+    "pn_table_fake_quant": [_P, _P, _I, _L, _P, _P],
     "pn_radam_step_dyn": [_P, _P, _P, _P, _L] + [ctypes.c_float] * 3 + [_P, _I, _P],
     "pn_store_floats": [_P, ctypes.POINTER(ctypes.c_float), _I, _P],
     "pn_composite_fwd": [_P, _I, _P, _P, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -79,10 +79,26 @@ def _check_tables(grid, tables):
         dptr(t)
 
 
+_QUANT_IN_GATHER = bool(os.environ.get("PN_QUANT_IN_GATHER"))      # A/B switch: fake-quant every gathered corner instead
+
+
+def quantized_tables(tables, qparams):
+    """The tables with each level's fake-quant row applied to every entry (pn_table_fake_quant): what the gather would
+    compute corner by corner, once per entry.  Returns a list of views of one fresh [L, T, 2] buffer."""
+    L, T = len(tables), tables[0].shape[0]
+    out = torch.empty((L, T, 2), dtype=torch.float32, device=tables[0].device)
+    outs = list(out.unbind(0))
+    with _guard(out):
+        call("pn_table_fake_quant", _ptr_array(tables), _ptr_array(outs), L, T, dptr(qparams), stream())
+    return outs
+
+
 def hash_encode_fwd(grid, tables, x, qparams=None):
     """x[P,3] -> feat[P,2L], keep[P] (bool).   Reference: hash_encoding.py:82-107."""
     x = fcontig(x)
     _check_tables(grid, tables)
+    if qparams is not None and not _QUANT_IN_GATHER and x.shape[0] > 0:
+        tables, qparams = quantized_tables(tables, qparams), None
     P = x.shape[0]
     feat = torch.empty((P, 2 * grid.n_levels), dtype=torch.float32, device=x.device)
     keep = torch.empty((P,), dtype=torch.bool, device=x.device)
@@ -517,10 +533,13 @@ class FieldFn(torch.autograd.Function):
             need_bwd = any(ctx.needs_input_grad[8:])     # all False under no_grad (render / eval): no feature tiles
             feat = torch.empty(((P + 127) // 128) * 8192, dtype=torch.uint8, device=pts.device) if need_bwd else None
             _check_tables(grid, tables)
+            ktabs, kq = [t.detach() for t in tables], qparams
+            if kq is not None and not _QUANT_IN_GATHER:
+                ktabs, kq = quantized_tables(ktabs, kq), None     # fake-quant per table entry, not per gathered corner
             with _guard(pts):
                 ws = _weights_struct(w)
-                _timed_call("pn_field_fwd_bf16", P, ctypes.byref(grid), _ptr_array([t.detach() for t in tables]),
-                     dptr(qparams, allow_none=True), ctypes.byref(ws), dptr(pts), dptr(dirs), int(S),
+                _timed_call("pn_field_fwd_bf16", P, ctypes.byref(grid), _ptr_array(ktabs),
+                     dptr(kq, allow_none=True), ctypes.byref(ws), dptr(pts), dptr(dirs), int(S),
                      dptr(act_q, allow_none=True), P, dptr(out), dptr(keep, torch.bool),
                      dptr(feat, torch.uint8, allow_none=True), stream())
             if feat is None:
