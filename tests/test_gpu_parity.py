@@ -156,6 +156,48 @@ def test_hash_quant_golden(pn, golden, mode):
     assert (keep.cpu().numpy() == g["keep"]).all()
 
 
+@pytest.mark.parametrize("train_form", [True, False])
+def test_table_level_fake_quant_equals_fake_quant_in_the_gather(pn, train_form):
+    """pn_table_fake_quant + plain gather == the gather that fake-quantises every corner value, bit for bit (fp32 kernels),
+    at T = 2^19 with some levels' quantisers off; the table copy equals the module's own quantiser on the entries."""
+    ops = pn.ops
+    log2T = 19
+    box = (np.array([-1.5, -1.0, -2.0], np.float32), np.array([1.5, 2.0, 1.0], np.float32))
+    emb = embedder_from(pn, box[0], box[1], log2T, 512, synthetic_tables(16, log2T, salt=3), use_quantization=True,
+                        quantization_bits=8)
+    rs = np.random.RandomState(4)
+    with torch.no_grad():
+        for q in emb.quantizers:
+            q.soft_bits.fill_(float(rs.uniform(3.2, 11.7)))
+            q.calibrate(emb.embeddings[0].weight.detach() * float(rs.uniform(0.5, 2.0)))
+    emb.train(train_form)
+    from indoor_nerf_b200.hash_encoding import qrows_batched
+    rows = qrows_batched(list(emb.quantizers), train_form).contiguous().clone()
+    rows[3, 5] = 0.0                                                # two levels with the quantiser switched off
+    rows[11, 5] = 0.0
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand(1 << 18, 3, device="cuda", generator=gen) * cu(box[1] - box[0]) + cu(box[0])
+    tables = [t.detach() for t in emb.tables()]
+    qt = ops.quantized_tables(tables, rows)
+    for l in (0, 3, 7, 15):
+        if float(rows[l, 5]) == 0.0:
+            assert torch.equal(qt[l], tables[l])
+        else:
+            q = emb.quantizers[l]
+            q.train(train_form)
+            with torch.no_grad():
+                assert torch.equal(qt[l], q(tables[l]))
+    was = ops._QUANT_IN_GATHER
+    try:
+        ops._QUANT_IN_GATHER = True
+        f_gather, k_gather = ops.hash_encode_fwd(emb.grid(), tables, x, rows)
+        ops._QUANT_IN_GATHER = False
+        f_table, k_table = ops.hash_encode_fwd(emb.grid(), tables, x, rows)
+    finally:
+        ops._QUANT_IN_GATHER = was
+    assert torch.equal(f_gather, f_table) and torch.equal(k_gather, k_table)
+
+
 def test_hash_large_properties(pn):
     """Full-size (T = 2^19, 2^22 points) checks that do not need the oracle: agreement with the oracle on a
     slice, linearity in the tables, and sum(dE_l) == sum(dfeat_l) because trilinear weights sum to 1."""
