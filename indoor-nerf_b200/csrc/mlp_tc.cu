@@ -367,9 +367,10 @@ __device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, 
   mask = m4[0] | (m4[1] << 8) | (m4[2] << 16) | (m4[3] << 24);
   if (qrow != nullptr) {
     const float scale = qrow[0], denom = qrow[1], zp = qrow[2], qmin = qrow[3], qmax = qrow[4];
+    const float rdenom = pn_div(1.0f, denom);
     const bool train_form = qrow[6] != 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fake_quant(v[j], scale, denom, zp, qmin, qmax, train_form);
+    for (int j = 0; j < 32; ++j) v[j] = fake_quant_rcp(v[j], scale, denom, rdenom, zp, qmin, qmax, train_form);
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) st_chunk(tile, chunk_off(p, half * 4 + c, 8), v + 8 * c);

@@ -6,6 +6,7 @@
 // -ffp-contract=off) behind a tiny C interface so that the CPU test-suite can check them against the
 // golden vectors without a GPU.  It is loaded by tests/test_hostemu.py only; the product library
 // (libpocketnerf.so) contains none of it and has no CPU path.
+#include <cstring>
 #include "../../indoor-nerf_b200/csrc/hash_core.cuh"
 #include "../../indoor-nerf_b200/csrc/ray_core.cuh"
 #include "../../indoor-nerf_b200/csrc/sample_core.cuh"
@@ -80,6 +81,27 @@ int64_t emu_cell_index_mismatches(const pn_hash_grid *grid, const float *x, int6
         fb += (fr < tol || fr > 1.0f - tol);
       }
     }
+  }
+  if (n_fallback) *n_fallback = fb;
+  return bad;
+}
+
+// fake_quant_rcp (reciprocal multiply + exact-division fallback) next to fake_quant: number of values whose results
+// differ in any bit (must be 0); *n_fallback = how often the fallback division was taken.
+int64_t emu_fake_quant_mismatches(const float *x, int64_t n, float scale, float denom, float zp, float qmin, float qmax,
+                                  int train_form, int64_t *n_fallback) {
+  const float rdenom = pn_div(1.0f, denom);
+  int64_t bad = 0, fb = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const float a = fake_quant(x[i], scale, denom, zp, qmin, qmax, train_form != 0);
+    const float b = fake_quant_rcp(x[i], scale, denom, rdenom, zp, qmin, qmax, train_form != 0);
+    uint32_t ua, ub;
+    memcpy(&ua, &a, 4);
+    memcpy(&ub, &b, 4);
+    bad += (ua != ub) && !(a != a && b != b);
+    const float p = pn_mul(x[i], rdenom), s = pn_add(p, zp);
+    const float tol = pn_mul(pn_add(fabsf(p), fabsf(s)), 2.384185791015625e-7f);
+    fb += fabsf(pn_sub(s, rintf(s))) >= pn_sub(0.5f, tol);
   }
   if (n_fallback) *n_fallback = fb;
   return bad;

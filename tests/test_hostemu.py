@@ -185,3 +185,39 @@ def test_fast_cell_index_equals_exact(emu, finest, box):
     assert bad == 0, "%d voxel indices differ between the fast and the exact form" % bad
     frac = nfb.value / (x.shape[0] * 16 * 3)
     assert 0 < frac < 0.25, "fallback rate %.4f (expected: rare on random points, common on the knife edges)" % frac
+
+
+@pytest.mark.parametrize("train_form", [0, 1])
+def test_division_free_fake_quant_equals_exact(emu, train_form):
+    """The tensor-core MLP quantises its hidden activations with fake_quant_rcp (reciprocal multiply, IEEE division only
+    near a rounding tie): it must return fake_quant's bits (quantization.py:177-187) everywhere — random activations,
+    values ON the rounding ties of x / denom + zp (and one ulp either side), values beyond the clamp range, inf / NaN."""
+    rng = np.random.default_rng(21)
+    emu.emu_fake_quant_mismatches.restype = ctypes.c_int64
+    f32 = ctypes.c_float
+    total_fb, total_n = 0, 0
+    for bits, vmax, zp_frac in ((8, 3.7, 0.0), (8, 0.0123, 0.37), (4, 11.0, 0.5), (12, 0.91, 0.123), (6, 250.0, 0.0),
+                                (10, 1e-3, 0.77)):
+        qmin, qmax = 0.0, float(2 ** bits - 1)
+        denom = np.float32(vmax / qmax)                       # the divisor; scale deliberately a different rounding of it
+        scale = np.float32(np.float32(vmax) / np.float32(qmax))
+        zp = np.float32(np.round(zp_frac * qmax) if zp_frac in (0.0, 0.5) else zp_frac * qmax)
+        xs = [rng.uniform(-0.2 * vmax, 1.3 * vmax, 300000).astype(np.float32),
+              (rng.standard_normal(100000) * vmax).astype(np.float32)]
+        k = rng.integers(-2, int(qmax) + 3, 20000).astype(np.float32)
+        tie = ((k + np.float32(0.5) - zp) * denom).astype(np.float32)       # x with x / denom + zp ~ k + 0.5
+        for d in range(-3, 4):
+            t = tie.copy()
+            for _ in range(abs(d)):
+                t = np.nextafter(t, np.float32(np.inf if d > 0 else -np.inf))
+            xs.append(t)
+        xs.append(np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e30, -1e30, 1e-40], np.float32))
+        x = np.ascontiguousarray(np.concatenate(xs))
+        nfb = ctypes.c_int64(0)
+        bad = emu.emu_fake_quant_mismatches(fptr(x), ctypes.c_int64(x.shape[0]), f32(scale), f32(denom), f32(zp), f32(qmin),
+                                            f32(qmax), ctypes.c_int(train_form), ctypes.byref(nfb))
+        assert bad == 0, "%d values differ between the division-free and the exact fake-quant (bits %d)" % (bad, bits)
+        total_fb += nfb.value
+        total_n += x.shape[0]
+    frac = total_fb / total_n
+    assert 0 < frac < 0.5, "fallback rate %.4f (expected: rare on random values, the rule on the ties)" % frac
