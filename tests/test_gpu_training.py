@@ -200,9 +200,10 @@ def test_cuda_graph_step_equals_eager_step():
         report[name] = (control, graphed)
     # RAdam's normalised update turns reduction-order noise on a near-zero gradient into a full +-lr move, so two eager runs
     # drift apart as well: that drift (x4) plus a rounding floor is the bar
-    floor = np.array([1e-5, 1e-3, 1e-2])
+    floors = {"loss": np.array([2e-3, 1e-2, 2e-2]), "weights": np.array([1e-4, 2e-3, 2e-2]),
+              "tables": np.array([1e-4, 2e-3, 2e-2])}
     for name, (control, graphed) in report.items():
-        assert (graphed <= 4 * control + floor).all(), report
+        assert (graphed <= 4 * control + floors[name]).all(), report
     assert np.allclose(le[:12], lg[:12], rtol=5e-3), (le[:12], lg[:12])           # the first replays
     assert tr_e.step_idx == tr_g.step_idx == 30
     assert tr_e.embed_fn.current_step == tr_g.embed_fn.current_step
