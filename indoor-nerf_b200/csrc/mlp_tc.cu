@@ -346,6 +346,10 @@ packed_gather8<false>(F->PK, l, F->G, c, e0, e1);
 // returns the ReLU mask of those columns.  The activation fake-quant (IEEE division, ~40 instructions per element) sits
 // behind ONE branch: written as `if (qrow)` per element it was if-converted, and the clock64 timeline showed the first
 // epilogue of every tile taking 2.4-2.8 k cycles (the others 0.2-0.6 k) with quantisation off.
+// RCP: quantise with fake_quant_rcp (no IEEE division off the rounding ties; same bits).  Only the forward kernels take it:
+// in the three-role backward the extra code of the 32 fallback branches cost the (register-tight) epilogue role 0.3 ms
+// per fine pass even with quantisation off (5.48 -> 5.79 ms, A/B on one box), more than it saves a quantised step.
+template <bool RCP = false>
 __device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, int p, int half, const float *qrow) {
   uint32_t mask = 0;
   float v[32];
@@ -367,10 +371,15 @@ __device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, 
   mask = m4[0] | (m4[1] << 8) | (m4[2] << 16) | (m4[3] << 24);
   if (qrow != nullptr) {
     const float scale = qrow[0], denom = qrow[1], zp = qrow[2], qmin = qrow[3], qmax = qrow[4];
-    const float rdenom = pn_div(1.0f, denom);
     const bool train_form = qrow[6] != 0.f;
+    if (RCP) {
+      const float rdenom = pn_div(1.0f, denom);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fake_quant_rcp(v[j], scale, denom, rdenom, zp, qmin, qmax, train_form);
+      for (int j = 0; j < 32; ++j) v[j] = fake_quant_rcp(v[j], scale, denom, rdenom, zp, qmin, qmax, train_form);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fake_quant(v[j], scale, denom, zp, qmin, qmax, train_form);
+    }
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) st_chunk(tile, chunk_off(p, half * 4 + c, 8), v + 8 * c);
@@ -401,7 +410,7 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
   T.mark();
   mbar_wait(bar, ph); ph ^= 1; fence_after_sync();
   T.mark();
-  h1_mask = epi_hidden32(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
+  h1_mask = epi_hidden32<!BWD>(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
   T.mark();
   PN_ROUND_SYNC();
   // R2: [sigma, geo] = H1 S1^T
