@@ -346,9 +346,10 @@ packed_gather8<false>(F->PK, l, F->G, c, e0, e1);
 // returns the ReLU mask of those columns.  The activation fake-quant (IEEE division, ~40 instructions per element) sits
 // behind ONE branch: written as `if (qrow)` per element it was if-converted, and the clock64 timeline showed the first
 // epilogue of every tile taking 2.4-2.8 k cycles (the others 0.2-0.6 k) with quantisation off.
-// RCP: quantise with fake_quant_rcp (no IEEE division off the rounding ties; same bits).  Only the forward kernels take it:
-// in the three-role backward the extra code of the 32 fallback branches cost the (register-tight) epilogue role 0.3 ms
-// per fine pass even with quantisation off (5.48 -> 5.79 ms, A/B on one box), more than it saves a quantised step.
+// RCP: quantise with fake_quant_rcp (no IEEE division off the rounding ties; same bits).  In the three-role backward the
+// extra code of its 32 fallback branches cost the (register-tight) epilogue role 0.3 ms per fine pass even with
+// quantisation OFF (5.48 -> 5.79 ms, A/B on one box): hence that kernel's ACTQ template parameter — builds without an
+// activation quantiser carry no quantiser code at all, builds with one use this form.
 template <bool RCP = false>
 __device__ __forceinline__ uint32_t epi_hidden32(uint32_t taddr, uint8_t *tile, int p, int half, const float *qrow) {
   uint32_t mask = 0;
@@ -889,7 +890,7 @@ static_assert(kV4ScatterWarps == 3 || kV4ScatterWarps == 7, "warps 8.. must fill
 // (fine pass) consecutive samples share voxels at most levels and SEG wins (5.41 -> 5.19 ms); with 64 samples per ray
 // (coarse pass) they rarely do and the 4-sample serial loop only costs parallelism (2.25 -> 2.67 ms) — so the launcher
 // picks SEG by samples_per_ray.
-template <bool NORMALS, bool SEG>
+template <bool NORMALS, bool SEG, bool ACTQ>
 __global__ void __launch_bounds__(kV4Threads, 2)
 field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const float *__restrict__ dout, const pn_mlp_grads G,
                   float *__restrict__ ring) {
@@ -1036,9 +1037,10 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
   setmaxnreg_inc<kV4EpiRegs>();
   const int p = tid & 127, half = tid >> 7;
   uint32_t ph = 0;
+  // ACTQ = false (no activation quantiser: every unquantised model) compiles the fake-quant out of the epilogue role
   float q[8];
   const float *qrow = nullptr;
-  if (A.in.act_q) {
+  if (ACTQ && A.in.act_q) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
     if (q[5] != 0.f) qrow = q;
@@ -1066,7 +1068,7 @@ field_bwd4_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, const flo
     epi_arrive(&ready, lane);
     // E1: H1 = relu(D1) -> A1
     epi_wait(&done, ph);
-    const uint32_t h1_mask = epi_hidden32(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);
+    const uint32_t h1_mask = epi_hidden32<true>(lane_addr + TM_D1, sm + TS::A1, p, half, qrow);   // quant code only in ACTQ builds
     epi_arrive(&ready, lane);
     // E2: [sigma, geo] -> CIN[16..32)
     epi_wait(&done, ph);
@@ -1346,10 +1348,11 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_bwd_kernel<SRC_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+#define PN_BWD4_ATTR(N, S, Q) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(field_bwd4_kernel<N, S, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+    PN_BWD4_ATTR(false, false, false); PN_BWD4_ATTR(false, true, false); PN_BWD4_ATTR(true, false, false); PN_BWD4_ATTR(true, true, false);
+    PN_BWD4_ATTR(false, false, true); PN_BWD4_ATTR(false, true, true); PN_BWD4_ATTR(true, false, true); PN_BWD4_ATTR(true, true, true);
+#undef PN_BWD4_ATTR
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_bwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
@@ -1368,10 +1371,19 @@ static int launch_tc_bwd(const TcArgs &A, const FieldArgs &F, bool fused, const 
     }
     const bool seg = A.in.samples_per_ray >= seg_min;
     float *ring = reinterpret_cast<float *>(workspace);
-    if (A.normals && seg) field_bwd4_kernel<true, true><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
-    else if (A.normals) field_bwd4_kernel<true, false><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
-    else if (seg) field_bwd4_kernel<false, true><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
-    else field_bwd4_kernel<false, false><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring);
+    const int variant = (A.normals ? 4 : 0) | (seg ? 2 : 0) | (A.in.act_q != nullptr ? 1 : 0);
+#define PN_BWD4_LAUNCH(N, S, Q) field_bwd4_kernel<N, S, Q><<<blocks, kV4Threads, smem, st>>>(A, F, dout, dw, ring)
+    switch (variant) {
+      case 0: PN_BWD4_LAUNCH(false, false, false); break;
+      case 1: PN_BWD4_LAUNCH(false, false, true); break;
+      case 2: PN_BWD4_LAUNCH(false, true, false); break;
+      case 3: PN_BWD4_LAUNCH(false, true, true); break;
+      case 4: PN_BWD4_LAUNCH(true, false, false); break;
+      case 5: PN_BWD4_LAUNCH(true, false, true); break;
+      case 6: PN_BWD4_LAUNCH(true, true, false); break;
+      default: PN_BWD4_LAUNCH(true, true, true); break;
+    }
+#undef PN_BWD4_LAUNCH
   } else if (fused)
     mlp_tc_bwd_kernel<SRC_TILE><<<blocks, kTcThreads, smem, st>>>(A, F, dout, dfeat, dfeat_stride, dsh, dsh_stride, dw);
   else
