@@ -248,7 +248,7 @@ constexpr int kTcThreads = 256;
 //             F.featb is set, also saved as bf16 tiles for the backward (pn_field_fwd_bf16)
 //   SRC_TILE: bf16 tile saved by the forward, copied as is (pn_field_bwd_bf16)
 //   SRC_PACKED: as SRC_HASH with the tables held as u8/u16 codes, decoded in the gather (pn_field_fwd_bf16_packed)
-template <int SRC>
+template <int SRC, bool GQ = true>
 __device__ __forceinline__ void tc_load_inputs(uint8_t *sm, const TcArgs &A, const FieldArgs *F, int64_t tile,
                                                int64_t base, int p, int half, bool valid) {
   if (SRC == SRC_F32) {
@@ -290,7 +290,7 @@ packed_gather8<false>(F->PK, l, F->G, c, e0, e1);
         } else {
           gather8<false>(F->G, F->T.t[l], c, e0, e1);
         }
-        if (SRC == SRC_HASH && F->qparams) {
+        if (GQ && SRC == SRC_HASH && F->qparams) {
           const float *q = F->qparams + l * PN_QROW;
           if (q[5] != 0.f) {
             const float scale = q[0], rdenom = 1.0f / q[1], zp = q[2], qmin = q[3], qmax = q[4];
@@ -478,7 +478,10 @@ __device__ __forceinline__ void tc_forward(uint8_t *sm, const TcArgs &A, uint32_
   PN_ROUND_SYNC();
 }
 
-template <int MIN_CTAS, int SRC>
+// QUANT = false: a build without any fake-quant code (no per-level rows in the gather, no activation quantiser) — what
+// every unquantised model runs, and quantised ones too unless the rows are passed to the gather (PN_QUANT_IN_GATHER)
+// or the MLP has an activation quantiser.
+template <int MIN_CTAS, int SRC, bool QUANT = true>
 __global__ void __launch_bounds__(kTcThreads, MIN_CTAS)
 mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__restrict__ out) {
   extern __shared__ __align__(128) uint8_t sm[];
@@ -495,7 +498,7 @@ mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__
   uint32_t ph = 0;
   float q[8];
   const float *qrow = nullptr;
-  if (A.in.act_q) {
+  if (QUANT && A.in.act_q) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) q[i] = __ldg(A.in.act_q + i);
     if (q[5] != 0.f) qrow = q;
@@ -511,7 +514,7 @@ mlp_tc_fwd_kernel(const TcArgs A, const __grid_constant__ FieldArgs F, float *__
       const uint32_t pb = (uint32_t)(rows * 12) & ~15u;
       if (pb && (((uintptr_t)(F.pts + nb * 3)) & 15) == 0) prefetch_l2(F.pts + nb * 3, pb);
     }
-    tc_load_inputs<SRC>(sm, A, &F, tile, base, p, half, valid);
+    tc_load_inputs<SRC, QUANT>(sm, A, &F, tile, base, p, half, valid);
     PN_ROUND_SYNC();
     float sigma = 0.f, nraw[3] = {0.f, 0.f, 0.f};
     uint32_t m;
@@ -1301,6 +1304,7 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
     fused_ctas = (e && atoi(e) == 4) ? 4 : 3;
   }
   const int per_sm = (A.normals || packed) ? 3 : (fused ? fused_ctas : 4);   // x 128 TMEM columns each
+  const bool quant = F.qparams != nullptr || A.in.act_q != nullptr;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1309,6 +1313,8 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<4, SRC_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<4, SRC_HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_HASH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<4, SRC_HASH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS::FWD_END);
     PN_REQUIRE(e == cudaSuccess, PN_ECUDA, "cudaFuncSetAttribute(mlp_tc_fwd): %s", cudaGetErrorString(e));
     attr_set[dev] = true;
@@ -1317,8 +1323,13 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int blocks = (int)(tiles < cap ? tiles : cap);
   if (packed) mlp_tc_fwd_kernel<3, SRC_PACKED><<<blocks, kTcThreads, smem, st>>>(A, F, out);
-  else if (fused && per_sm == 4) mlp_tc_fwd_kernel<4, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
-  else if (fused) mlp_tc_fwd_kernel<3, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  else if (fused && per_sm == 4 && quant) mlp_tc_fwd_kernel<4, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  else if (fused && per_sm == 4)      // no normal head (per_sm): its hidden tile, the last region of the map, is never touched,
+    // so 54 KB per CTA and four really are resident — measured slower (fine pass 2.34 -> 2.72 ms, coarse 1.14 -> 1.96):
+    // 4 x 54 KB of shared memory leave the gather almost no L1
+    mlp_tc_fwd_kernel<4, SRC_HASH, false><<<blocks, kTcThreads, TS::NH, st>>>(A, F, out);
+  else if (fused && quant) mlp_tc_fwd_kernel<3, SRC_HASH><<<blocks, kTcThreads, smem, st>>>(A, F, out);
+  else if (fused) mlp_tc_fwd_kernel<3, SRC_HASH, false><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   else if (A.normals) mlp_tc_fwd_kernel<3, SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   else mlp_tc_fwd_kernel<4, SRC_F32><<<blocks, kTcThreads, smem, st>>>(A, F, out);
   count_launch();
