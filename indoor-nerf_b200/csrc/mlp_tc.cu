@@ -1301,7 +1301,9 @@ static int launch_tc_fwd(const TcArgs &A, const FieldArgs &F, bool fused, float 
   static int fused_ctas = -1;
   if (fused_ctas < 0) {                                  // tuning knob
     const char *e = getenv("PN_FWD_CTAS");
-    fused_ctas = (e && atoi(e) == 4) ? 4 : 3;
+    fused_ctas = (e && atoi(e) == 4) ? 4 : ((e && atoi(e) == 2) ? 2 : 3);
+    if (fused_ctas == 2)     // two resident CTAs and the rest of the SM's 256 KB as L1 (measurement knob)
+      cudaFuncSetAttribute(mlp_tc_fwd_kernel<3, SRC_HASH, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
   }
   const int per_sm = (A.normals || packed) ? 3 : (fused ? fused_ctas : 4);   // x 128 TMEM columns each
   const bool quant = F.qparams != nullptr || A.in.act_q != nullptr;
