@@ -65,13 +65,16 @@ __device__ __forceinline__ void ray_forward(const float *__restrict__ raw, int C
 #ifndef PN_COMP_FWD_MINB
 #define PN_COMP_FWD_MINB 8     // 64 registers: 32 warps per SM hide the scan and exp latency (0.23 -> 0.17 ms at 65536 x 192)
 #endif
-template <int K>
+// N7: the raw rows carry a normal (7 channels); false compiles the normal map out (C == 4)
+template <int K, bool N7>
 __global__ void __launch_bounds__(kRayWarps * 32, PN_COMP_FWD_MINB)
-composite_fwd_kernel(const float *__restrict__ raw, int C, const float *__restrict__ z,
+composite_fwd_kernel(const float *__restrict__ raw, int C_, const float *__restrict__ z,
                      const float *__restrict__ rays_d, const float *__restrict__ noise, int64_t N, int S,
                      int white, int vec4, float *__restrict__ rgb, float *__restrict__ disp, float *__restrict__ acc,
                      float *__restrict__ weights, float *__restrict__ depth, float *__restrict__ sparsity,
                      float *__restrict__ normal) {
+  const int C = N7 ? 7 : 4;
+  (void)C_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t r = (int64_t)blockIdx.x * kRayWarps + warp; r < N; r += (int64_t)gridDim.x * kRayWarps) {
     RayState<K> st;
@@ -138,14 +141,16 @@ composite_fwd_kernel(const float *__restrict__ raw, int C, const float *__restri
 #ifndef PN_COMP_BWD_MINB
 #define PN_COMP_BWD_MINB 5     // measured: 5 blocks x 4 warps (<= 102 registers) beats 3 (143) and 6 (85, spills)
 #endif
-template <int K>
+template <int K, bool N7>
 __global__ void __launch_bounds__(kRayWarps * 32, K <= 6 ? PN_COMP_BWD_MINB : 3)
-composite_bwd_kernel(const float *__restrict__ raw, int C, const float *__restrict__ z,
+composite_bwd_kernel(const float *__restrict__ raw, int C_, const float *__restrict__ z,
                      const float *__restrict__ rays_d, const float *__restrict__ noise, int64_t N, int S,
                      int white, int vec4, const float *__restrict__ d_rgb, const float *__restrict__ d_disp,
                      const float *__restrict__ d_acc, const float *__restrict__ d_weights,
                      const float *__restrict__ d_depth, const float *__restrict__ d_sparsity,
                      const float *__restrict__ d_normal, float *__restrict__ draw) {
+  const int C = N7 ? 7 : 4;
+  (void)C_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t r = (int64_t)blockIdx.x * kRayWarps + warp; r < N; r += (int64_t)gridDim.x * kRayWarps) {
     RayState<K> st;
@@ -318,10 +323,16 @@ extern "C" int pn_composite_fwd(const float *raw, int channels, const float *z, 
   if (n_rays <= 0) return 0;
   const int vec4 = channels == 4 && ((uintptr_t)raw & 15) == 0;       // 16-byte rows: one load per sample
 #define CALL(K)                                                                                          \
-  composite_fwd_kernel<K><<<ray_blocks(n_rays, composite_fwd_kernel<K>), kRayWarps * 32, 0, as_stream(stream)>>>(                            \
+  composite_fwd_kernel<K, N7><<<ray_blocks(n_rays, composite_fwd_kernel<K, N7>), kRayWarps * 32, 0, as_stream(stream)>>>(                            \
       raw, channels, z, rays_d, noise, n_rays, n_samples, white_bkgd, vec4, rgb, disp, acc, weights, depth, \
       sparsity, normal)
-  PN_DISPATCH_K(n_samples, CALL);
+  if (channels == 7) {
+    constexpr bool N7 = true;
+    PN_DISPATCH_K(n_samples, CALL);
+  } else {
+    constexpr bool N7 = false;
+    PN_DISPATCH_K(n_samples, CALL);
+  }
 #undef CALL
   count_launch();
   return check_launch("composite_fwd_kernel");
@@ -338,10 +349,16 @@ extern "C" int pn_composite_bwd(const float *raw, int channels, const float *z, 
   if (n_rays <= 0) return 0;
   const int vec4 = channels == 4 && (((uintptr_t)raw | (uintptr_t)draw) & 15) == 0;
 #define CALL(K)                                                                                        \
-  composite_bwd_kernel<K><<<ray_blocks(n_rays, composite_bwd_kernel<K>), kRayWarps * 32, 0, as_stream(stream)>>>(                          \
+  composite_bwd_kernel<K, N7><<<ray_blocks(n_rays, composite_bwd_kernel<K, N7>), kRayWarps * 32, 0, as_stream(stream)>>>(                          \
       raw, channels, z, rays_d, noise, n_rays, n_samples, white_bkgd, vec4, d_rgb, d_disp, d_acc, d_weights, \
       d_depth, d_sparsity, d_normal, draw)
-  PN_DISPATCH_K(n_samples, CALL);
+  if (channels == 7) {
+    constexpr bool N7 = true;
+    PN_DISPATCH_K(n_samples, CALL);
+  } else {
+    constexpr bool N7 = false;
+    PN_DISPATCH_K(n_samples, CALL);
+  }
 #undef CALL
   count_launch();
   return check_launch("composite_bwd_kernel");
