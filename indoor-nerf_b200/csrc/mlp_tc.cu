@@ -888,8 +888,11 @@ constexpr int kV4Threads = kTcThreads + 32 + 32 * kV4ScatterWarps;
 // longer spills (fine-pass backward 5.66 -> 5.57 ms kernel-only; 88 / 40 was 7.25 ms).
 template <bool ACTQ>
 struct V4Regs {
-  static constexpr int epi = kV4ScatterWarps == 3 ? 88 : (ACTQ ? 80 : 72);
-  static constexpr int aux = kV4ScatterWarps == 3 ? 64 : (ACTQ ? 48 : 56);
+#ifndef PN_V4_EPI_NOQ
+#define PN_V4_EPI_NOQ 72
+#endif
+  static constexpr int epi = kV4ScatterWarps == 3 ? 88 : (ACTQ ? 80 : PN_V4_EPI_NOQ);
+  static constexpr int aux = kV4ScatterWarps == 3 ? 64 : (ACTQ ? 48 : 128 - PN_V4_EPI_NOQ);
 };
 constexpr int kRingSlots = 4;
 static_assert(kV4ScatterWarps == 3 || kV4ScatterWarps == 7, "warps 8.. must fill whole warpgroups (setmaxnreg)");
